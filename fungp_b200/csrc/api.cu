@@ -1,0 +1,720 @@
+// C ABI of libfungp_b200.so (include/fungp_b200.h): contexts, problems and the likelihood / prediction /
+// simulation / LOOCV entry points.  No CPU fallback: every numeric path launches the sm_100a kernels.
+#include "ctx.h"
+#include "../../include/fungp_b200.h"
+#include <cstring>
+#include <thread>
+
+// ------------------------------------------------------------------------------------------------ errors
+void fgp_set_err(fgp_ctx* ctx, const std::string& msg) {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err = msg;
+}
+void fgp_set_err_cuda(fgp_ctx* ctx, const char* what, cudaError_t e, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    fgp_set_err(ctx, buf);
+    cudaGetLastError();
+}
+#define CK(expr)                                                              \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            fgp_set_err_cuda(ctx, #expr, _e, __FILE__, __LINE__);             \
+            return FGP_ERR_CUDA;                                              \
+        }                                                                     \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline long roundup(long a, long b) { return (a + b - 1) / b * b; }
+// leading dimension: multiple of 16 doubles (128 B); avoid large power-of-two strides
+static inline long pick_ld(long rows) {
+    long ld = roundup(rows, 16);
+    if (ld % 512 == 0) ld += 16;
+    return ld;
+}
+
+extern "C" const char* fgp_version(void) { return "fungp_b200 0.1 (sm_100a, FP64 DMMA)"; }
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int fgp_ctx_create(int n_devices, const int* device_ids, fgp_ctx** out) {
+    if (!out) return FGP_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return FGP_ERR_NODEVICE;   // no CPU fallback by design
+    }
+    if (n_devices <= 0) n_devices = count;
+    if (n_devices > FGP_MAXDEV) n_devices = FGP_MAXDEV;
+    fgp_ctx* ctx = new fgp_ctx();
+    ctx->dev.resize(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        DevState& d = ctx->dev[i];
+        d.device = device_ids ? device_ids[i] : i;
+        if (d.device < 0 || d.device >= count) { delete ctx; return FGP_ERR_ARG; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d.device) != cudaSuccess || prop.major < 10) {
+            // the kernels are sm_100a only
+            delete ctx;
+            return FGP_ERR_NODEVICE;
+        }
+        if (cudaSetDevice(d.device) != cudaSuccess) { delete ctx; return FGP_ERR_CUDA; }
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int s = 0; s < DevState::MAXSTREAMS; ++s) {
+            cudaStreamCreateWithPriority(&d.sPanel[s], cudaStreamNonBlocking, hi);   // panel = critical path
+            cudaEventCreateWithFlags(&d.evJoin[s], cudaEventDisableTiming);
+        }
+        cudaStreamCreateWithPriority(&d.sBulk, cudaStreamNonBlocking, lo);
+        cudaEventCreateWithFlags(&d.evA, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d.evB, cudaEventDisableTiming);
+    }
+    cudaSetDevice(ctx->dev[0].device);
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->dev) {
+        cudaSetDevice(d.device);
+        cudaDeviceSynchronize();
+        for (int s = 0; s < DevState::MAXSTREAMS; ++s) {
+            if (d.sPanel[s]) cudaStreamDestroy(d.sPanel[s]);
+            if (d.evJoin[s]) cudaEventDestroy(d.evJoin[s]);
+        }
+        if (d.sBulk) cudaStreamDestroy(d.sBulk);
+        if (d.evA) cudaEventDestroy(d.evA);
+        if (d.evB) cudaEventDestroy(d.evB);
+        d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release();
+        if (d.pinned) cudaFreeHost(d.pinned);
+    }
+    delete ctx;
+}
+
+extern "C" int fgp_ctx_device_count(const fgp_ctx* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+extern "C" const char* fgp_last_error(const fgp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
+    if (!ctx || !name) return FGP_ERR_ARG;
+    if (!strcmp(name, "profile")) ctx->profile = value != 0;
+    else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
+    else if (!strcmp(name, "streams")) ctx->streams = std::max(1, std::min((int)value, (int)DevState::MAXSTREAMS));
+    else { fgp_set_err(ctx, std::string("unknown option ") + name); return FGP_ERR_ARG; }
+    return 0;
+}
+
+extern "C" int fgp_get_timing(fgp_ctx* ctx, double* out8) {
+    if (!ctx || !out8) return FGP_ERR_ARG;
+    DevState& d = ctx->dev[0];
+    cudaSetDevice(d.device);
+    double ms[FgpTimers::NCLASS], cnt[FgpTimers::NCLASS], fl[FgpTimers::NCLASS];
+    d.timers.collect(ms, cnt, fl);
+    out8[0] = ms[FgpTimers::ASSEMBLY];
+    out8[1] = ms[FgpTimers::FACTOR];
+    out8[2] = ms[FgpTimers::UPDATE];
+    out8[3] = cnt[FgpTimers::UPDATE];
+    out8[4] = fl[FgpTimers::UPDATE];
+    out8[5] = ms[FgpTimers::PANEL];
+    out8[6] = cnt[FgpTimers::UPDATE] + cnt[FgpTimers::PANEL] + cnt[FgpTimers::ASSEMBLY];
+    out8[7] = cnt[FgpTimers::ASSEMBLY];
+    return 0;
+}
+
+extern "C" int fgp_measure_peaks(fgp_ctx* ctx, double* dmma_tflops, double* dfma_tflops, double* copy_gbs) {
+    if (!ctx) return FGP_ERR_ARG;
+    cudaSetDevice(ctx->dev[0].device);
+    return fgp_peaks_device(dmma_tflops, dfma_tflops, copy_gbs);
+}
+
+// ------------------------------------------------------------------------------------------------ problem
+void build_coords(const fgp_problem* P, int m, const double* sIn, const double* const* coefs, std::vector<double>& X) {
+    X.assign((size_t)m * P->ncoord, 0.0);
+    int col = 0;
+    for (int s = 0; s < P->ds; ++s, ++col) memcpy(&X[(size_t)col * m], sIn + (size_t)s * m, sizeof(double) * m);
+    for (int i = 0; i < P->df; ++i) {
+        const int p = P->p[i];
+        const double* c = coefs[i];
+        if (P->dis[i] == FGP_DIST_BYINDEX) {
+            for (int a = 0; a < p; ++a, ++col) memcpy(&X[(size_t)col * m], c + (size_t)a * m, sizeof(double) * m);
+        } else {
+            if (col & 1) ++col;   // group units start on an even column (they are staged as pairs)
+            const double* J = P->J[i].data();
+            for (int a = 0; a < p; ++a, col += 2) {
+                memcpy(&X[(size_t)col * m], c + (size_t)a * m, sizeof(double) * m);
+                double* e = &X[(size_t)(col + 1) * m];
+                // (f J)[, a] = sum_b f[, b] J[b, a]      (R/7_distanceFunctions.R:39-40)
+                for (int b = 0; b < p; ++b) {
+                    const double jba = J[b + (size_t)a * p];
+                    const double* cb = c + (size_t)b * m;
+                    for (int r = 0; r < m; ++r) e[r] += cb[r] * jba;
+                }
+            }
+        }
+    }
+}
+
+void kernel_scales(int ker, int nterms, const double* theta, double* scale) {
+    const double c = ker == FGP_KER_GAUSS ? 1.0 : (ker == FGP_KER_MATERN52 ? sqrt(5.0) : sqrt(3.0));
+    for (int t = 0; t < nterms; ++t) scale[t] = c / theta[t];
+}
+
+int problem_upload(fgp_problem* P, int slot) {
+    fgp_ctx* ctx = P->ctx;
+    ProblemDev& pd = P->pd[slot];
+    if (pd.ready) return 0;
+    CK(cudaSetDevice(ctx->dev[slot].device));
+    CK(cudaMalloc(&pd.X, sizeof(double) * std::max<size_t>(1, P->X.size())));
+    CK(cudaMalloc(&pd.units, sizeof(FgpUnit) * std::max<size_t>(1, P->units.size())));
+    CK(cudaMalloc(&pd.y, sizeof(double) * P->n));
+    CK(cudaMemcpy(pd.X, P->X.data(), sizeof(double) * P->X.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd.units, P->units.data(), sizeof(FgpUnit) * P->units.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pd.y, P->y.data(), sizeof(double) * P->n, cudaMemcpyHostToDevice));
+    pd.ready = true;
+    return 0;
+}
+
+extern "C" int fgp_problem_create(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* p,
+                                  const int* dis_type, const double* const* coefs, const double* const* J,
+                                  const double* y, fgp_problem** out) {
+    if (!ctx || !out || n <= 0 || ds < 0 || df < 0 || (ds == 0 && df == 0) || !y) return FGP_ERR_ARG;
+    if ((ds > 0 && !sIn) || (df > 0 && (!p || !dis_type || !coefs || !J))) return FGP_ERR_ARG;
+    *out = nullptr;
+    std::unique_ptr<fgp_problem> P(new fgp_problem());
+    P->ctx = ctx; P->n = n; P->ds = ds; P->df = df;
+    int col = 0, term = 0;
+    for (int s = 0; s < ds; ++s) {
+        P->termFirstUnit.push_back((int)P->units.size());
+        P->units.push_back({0, col++, term++, 1});
+    }
+    for (int i = 0; i < df; ++i) {
+        if (p[i] <= 0 || (dis_type[i] != FGP_DIST_BYGROUP && dis_type[i] != FGP_DIST_BYINDEX)) {
+            fgp_set_err(ctx, "fgp_problem_create: p[i] must be the number of coefficient columns (> 0) and dis_type 1|2");
+            return FGP_ERR_ARG;
+        }
+        P->p.push_back(p[i]); P->dis.push_back(dis_type[i]);
+        P->J.emplace_back(J[i], J[i] + (size_t)p[i] * p[i]);
+        if (dis_type[i] == FGP_DIST_BYINDEX) {
+            for (int a = 0; a < p[i]; ++a) {
+                P->termFirstUnit.push_back((int)P->units.size());
+                P->units.push_back({0, col++, term++, 1});
+            }
+        } else {
+            if (col & 1) ++col;
+            P->termFirstUnit.push_back((int)P->units.size());
+            for (int a = 0; a < p[i]; ++a, col += 2) P->units.push_back({1, col, term, a == p[i] - 1});
+            ++term;
+        }
+    }
+    P->termFirstUnit.push_back((int)P->units.size());
+    P->nterms = term; P->ncoord = col;
+    build_coords(P.get(), n, sIn, coefs, P->X);
+    P->y.assign(y, y + n);
+    P->pd.resize(ctx->dev.size());
+    int rc = problem_upload(P.get(), 0);
+    if (rc) return rc;
+    *out = P.release();
+    return 0;
+}
+
+extern "C" void fgp_problem_destroy(fgp_problem* P) {
+    if (!P) return;
+    for (size_t s = 0; s < P->pd.size(); ++s) {
+        ProblemDev& pd = P->pd[s];
+        if (!pd.ready && !pd.Lfac) continue;
+        cudaSetDevice(P->ctx->dev[s].device);
+        cudaDeviceSynchronize();
+        if (pd.X) cudaFree(pd.X);
+        if (pd.units) cudaFree(pd.units);
+        if (pd.y) cudaFree(pd.y);
+        if (pd.Lfac) cudaFree(pd.Lfac);
+        if (pd.Wall) cudaFree(pd.Wall);
+    }
+    delete P;
+}
+
+extern "C" int fgp_problem_n(const fgp_problem* P) { return P ? P->n : 0; }
+extern "C" int fgp_problem_nls(const fgp_problem* P) { return P ? P->nterms : 0; }
+
+extern "C" int fgp_problem_set_y(fgp_problem* P, const double* y) {
+    if (!P || !y) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    P->y.assign(y, y + P->n);
+    for (size_t s = 0; s < P->pd.size(); ++s)
+        if (P->pd[s].ready) {
+            CK(cudaSetDevice(ctx->dev[s].device));
+            CK(cudaMemcpy(P->pd[s].y, y, sizeof(double) * P->n, cudaMemcpyHostToDevice));
+        }
+    P->hasModel = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ distances
+extern "C" int fgp_dist_max(fgp_problem* P, double* max_out) {
+    if (!P || !max_out) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    if (d.small.ensure(sizeof(double) * std::max(1, P->nterms))) return FGP_ERR_ALLOC;
+    double* dmax = (double*)d.small.p;
+    CK(cudaMemsetAsync(dmax, 0, sizeof(double) * P->nterms, d.sPanel[0]));
+    const int n = P->n;
+    for (int t = 0; t < P->nterms; ++t) {
+        const int u0 = P->termFirstUnit[t], u1 = P->termFirstUnit[t + 1];
+        if (P->units[u0].kind == 1)
+            launch_distmax(P->pd[0].X, n, n, P->pd[0].units, u0, u1, dmax + t, d.sPanel[0]);
+    }
+    std::vector<double> h(P->nterms);
+    CK(cudaMemcpyAsync(h.data(), dmax, sizeof(double) * P->nterms, cudaMemcpyDeviceToHost, d.sPanel[0]));
+    CK(cudaStreamSynchronize(d.sPanel[0]));
+    for (int t = 0; t < P->nterms; ++t) {
+        const FgpUnit& u = P->units[P->termFirstUnit[t]];
+        if (u.kind == 1) max_out[t] = h[t];
+        else {
+            // max |x_i - x_j| = max - min of the column (abs(outer(-)), R/7_distanceFunctions.R:31)
+            const double* x = &P->X[(size_t)u.col * n];
+            double lo = x[0], hi = x[0];
+            for (int i = 1; i < n; ++i) { lo = std::min(lo, x[i]); hi = std::max(hi, x[i]); }
+            max_out[t] = hi - lo;
+        }
+    }
+    return 0;
+}
+
+extern "C" int fgp_dist_materialize(fgp_problem* P, int l, double* out) {
+    if (!P || !out || l < 0 || l >= P->nterms) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    const int n = P->n;
+    if (d.work.ensure(sizeof(double) * (size_t)n * n)) return FGP_ERR_ALLOC;
+    launch_distmat(P->pd[0].X, n, n, P->pd[0].units, P->termFirstUnit[l], P->termFirstUnit[l + 1], (double*)d.work.p, n,
+                   d.sPanel[0]);
+    CK(cudaMemcpyAsync(out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, d.sPanel[0]));
+    CK(cudaStreamSynchronize(d.sPanel[0]));
+    return 0;
+}
+
+static AsmArgs train_asm(const fgp_problem* P, const ProblemDev& pd, int ker, const double* scale_dev) {
+    AsmArgs a{};
+    a.XP = pd.X; a.nP = P->n; a.ldP = P->n;
+    a.XQ = pd.X; a.nQ = P->n; a.ldQ = P->n;
+    a.units = pd.units; a.nunits = (int)P->units.size();
+    a.scale = scale_dev; a.nterms = P->nterms; a.ker = ker; a.sym = 1;
+    a.mult = 1.0; a.diag_rel = 0.0; a.diag_abs = 0.0;
+    a.rowOff = 0; a.colOff = 0; a.mirror = 0;
+    return a;
+}
+
+extern "C" int fgp_assemble(fgp_problem* P, int ker, double nugget, const double* theta, double* R_out) {
+    if (!P || !theta || !R_out || ker < 1 || ker > 3) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    const int n = P->n;
+    if (d.work.ensure(sizeof(double) * (size_t)n * n)) return FGP_ERR_ALLOC;
+    if (d.small.ensure(sizeof(double) * P->nterms)) return FGP_ERR_ALLOC;
+    std::vector<double> sc(P->nterms);
+    kernel_scales(ker, P->nterms, theta, sc.data());
+    cudaStream_t st = d.sPanel[0];
+    CK(cudaMemcpyAsync(d.small.p, sc.data(), sizeof(double) * P->nterms, cudaMemcpyHostToDevice, st));
+    AsmArgs a = train_asm(P, P->pd[0], ker, (const double*)d.small.p);
+    a.diag_rel = nugget; a.M = (double*)d.work.p; a.ld = n; a.strideM = 0; a.mirror = 1;
+    launch_assemble(a, 1, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(R_out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ likelihood
+// one device's share of a batch: points [b0, b1)
+static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, int b1, const double* thetas,
+                     const double* var_known, double* nll, double* sig2, int* info) {
+    fgp_ctx* ctx = P->ctx;
+    DevState& d = ctx->dev[slot];
+    CK(cudaSetDevice(d.device));
+    int rc = problem_upload(P, slot);
+    if (rc) return rc;
+    const ProblemDev& pd = P->pd[slot];
+    const int n = P->n, nt = P->nterms, B = b1 - b0;
+    if (B <= 0) return 0;
+    const long ld = pick_ld(n + 1);
+    const size_t matBytes = sizeof(double) * (size_t)ld * n;
+    const int ncT = cdiv(n, FGP_TILE);
+    const size_t wBytes = sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE;
+    size_t freeB = 0, totB = 0;
+    cudaMemGetInfo(&freeB, &totB);
+    size_t budget = std::min<size_t>((size_t)((freeB + d.work.cap + d.wbuf.cap) * 0.6), (size_t)32 << 30);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, budget / (matBytes + wBytes)));
+    chunk = std::min(chunk, 4096);
+    if (d.work.ensure(matBytes * chunk) || d.wbuf.ensure(wBytes * chunk)) {
+        fgp_set_err(ctx, "fgp_nll_batch: out of device memory");
+        return FGP_ERR_ALLOC;
+    }
+    // small buffer: scales [chunk*nt] | nll [chunk] | sig2 [chunk] | var_known [1] | info [chunk]
+    const size_t smallBytes = sizeof(double) * ((size_t)chunk * nt + 2 * (size_t)chunk + 1) + sizeof(int) * chunk;
+    if (d.small.ensure(smallBytes)) return FGP_ERR_ALLOC;
+    double* dScale = (double*)d.small.p;
+    double* dNll = dScale + (size_t)chunk * nt;
+    double* dSig = dNll + chunk;
+    double* dVar = dSig + chunk;
+    int* dInfo = (int*)(dVar + 1);
+    std::vector<double> hScale((size_t)chunk * nt);
+    const bool prof = ctx->profile != 0;
+    if (prof) d.timers.reset();
+    if (var_known) CK(cudaMemcpy(dVar, var_known, sizeof(double), cudaMemcpyHostToDevice));
+
+    for (int c0 = 0; c0 < B; c0 += chunk) {
+        const int cb = std::min(chunk, B - c0);
+        for (int i = 0; i < cb; ++i) kernel_scales(ker, nt, thetas + (size_t)(b0 + c0 + i) * nt, &hScale[(size_t)i * nt]);
+        CK(cudaMemcpy(dScale, hScale.data(), sizeof(double) * (size_t)cb * nt, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dInfo, 0, sizeof(int) * cb));
+        // split the chunk over streams so that one group's panel phase overlaps another group's trailing update
+        int ns = prof ? 1 : std::min(ctx->streams, cb);
+        if ((long)n * n < 512L * 512L) ns = 1;   // tiny matrices: one batched launch sequence is enough
+        const int per = cdiv(cb, ns);
+        for (int s = 0; s < ns; ++s) {
+            const int g0 = s * per, g1 = std::min(cb, g0 + per);
+            if (g1 <= g0) continue;
+            const int gb = g1 - g0;
+            cudaStream_t st = d.sPanel[s];
+            double* Mg = (double*)d.work.p + (size_t)g0 * ld * n;
+            AsmArgs a = train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
+            a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
+            if (prof) d.timers.begin(st);
+            launch_assemble(a, gb, st);
+            if (prof) d.timers.end(st, FgpTimers::ASSEMBLY, 0.0);
+            launch_fill_yrow(Mg, ld, (long)ld * n, gb, n, pd.y, n, st);
+            TrapDesc t{};
+            t.M = Mg; t.ld = ld; t.strideM = (long)ld * n; t.batch = gb;
+            t.ncols = n; t.nrows = n + 1; t.holeLo = n + 1; t.holeHi = n + 1;
+            t.colHoleLo = n; t.colHoleHi = n; t.cpre = 0; t.upperRows = 0;
+            t.W = (double*)d.wbuf.p + (size_t)g0 * ncT * FGP_TILE * FGP_TILE; t.strideW = (long)ncT * FGP_TILE * FGP_TILE;
+            t.info = dInfo + g0;
+            if (prof) d.timers.begin(st);
+            cudaEvent_t fa = prof ? d.timers.cur : nullptr;
+            rc = trap_factor(ctx, slot, t, st, d.sBulk, ctx->lookahead && ns == 1 && gb == 1);
+            if (rc) return rc;
+            if (prof) { d.timers.cur = fa; d.timers.end(st, FgpTimers::FACTOR, 0.0); }
+            launch_nll_reduce(Mg, ld, (long)ld * n, gb, n, n, var_known ? dVar : nullptr, dInfo + g0, dNll + g0, dSig + g0, st);
+        }
+        for (int s = 0; s < ns; ++s) CK(cudaStreamSynchronize(d.sPanel[s]));
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(nll + b0 + c0, dNll, sizeof(double) * cb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(sig2 + b0 + c0, dSig, sizeof(double) * cb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(info + b0 + c0, dInfo, sizeof(int) * cb, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int fgp_nll_batch(fgp_problem* P, int ker, double nugget, int B, const double* thetas,
+                             const double* var_known, double* nll, double* sig2, int* info) {
+    if (!P || B < 0 || !thetas || !nll || !sig2 || !info || ker < 1 || ker > 3) return FGP_ERR_ARG;
+    if (B == 0) return 0;
+    fgp_ctx* ctx = P->ctx;
+    for (long i = 0; i < (long)B * P->nterms; ++i)
+        if (!(thetas[i] > 0.0)) { fgp_set_err(ctx, "fgp_nll_batch: length-scales must be > 0"); return FGP_ERR_ARG; }
+    const int nd = (int)ctx->dev.size();
+    if (nd == 1 || B == 1) return nll_range(P, 0, ker, nugget, 0, B, thetas, var_known, nll, sig2, info);
+    // independent points: contiguous shares per GPU, one host thread each, host-side gather (no collective)
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::thread> th;
+    for (int s = 0; s < nd; ++s) {
+        const int b0 = (int)((long)B * s / nd), b1 = (int)((long)B * (s + 1) / nd);
+        th.emplace_back([=, &rcs]() { rcs[s] = nll_range(P, s, ker, nugget, b0, b1, thetas, var_known, nll, sig2, info); });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->dev[0].device);
+    for (int s = 0; s < nd; ++s) if (rcs[s]) return rcs[s];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ preMats
+extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, const double* theta, double* L_out,
+                           double* LInvY_out) {
+    if (!P || !theta || ker < 1 || ker > 3 || !(sig2 > 0.0)) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    ProblemDev& pd = P->pd[0];
+    const int n = P->n, nt = P->nterms;
+    const long ld = pick_ld(n + 1);
+    const int ncT = cdiv(n, FGP_TILE);
+    if (!pd.Lfac) {
+        CK(cudaMalloc(&pd.Lfac, sizeof(double) * (size_t)ld * n));
+        CK(cudaMalloc(&pd.Wall, sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE));
+        pd.ldL = ld;
+    }
+    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
+    std::vector<double> sc(nt);
+    kernel_scales(ker, nt, theta, sc.data());
+    cudaStream_t st = d.sPanel[0];
+    double* dScale = (double*)d.small.p;
+    int* dInfo = (int*)(dScale + nt);
+    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
+    AsmArgs a = train_asm(P, pd, ker, dScale);
+    a.mult = sig2; a.diag_rel = nugget; a.M = pd.Lfac; a.ld = ld; a.strideM = 0;
+    launch_assemble(a, 1, st);
+    launch_fill_yrow(pd.Lfac, ld, 0, 1, n, pd.y, n, st);
+    TrapDesc t{};
+    t.M = pd.Lfac; t.ld = ld; t.strideM = 0; t.batch = 1;
+    t.ncols = n; t.nrows = n + 1; t.holeLo = n + 1; t.holeHi = n + 1; t.colHoleLo = n; t.colHoleHi = n;
+    t.cpre = 0; t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
+    int rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
+    if (rc) return rc;
+    int hinfo = 0;
+    CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hinfo != 0) { P->hasModel = false; return hinfo; }
+    P->hasModel = true; P->ker = ker; P->nugget = nugget; P->sig2 = sig2;
+    P->theta.assign(theta, theta + nt);
+    if (LInvY_out)
+        CK(cudaMemcpy2D(LInvY_out, sizeof(double), pd.Lfac + n, sizeof(double) * ld, sizeof(double), n, cudaMemcpyDeviceToHost));
+    if (L_out) {
+        if (d.work.ensure(sizeof(double) * (size_t)n * n)) return FGP_ERR_ALLOC;
+        launch_extract_lower(pd.Lfac, ld, n, (double*)d.work.p, st);
+        CK(cudaMemcpyAsync(L_out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// shared prologue of predict / simulate: workspace with L copied in, new-point coordinates uploaded
+struct NewPts {
+    double* Xnew = nullptr;   // m x ncoord on device
+};
+static int upload_new(fgp_problem* P, DevState& d, int m, const double* sNew, const double* const* coefsNew,
+                      double** Xnew_dev) {
+    fgp_ctx* ctx = P->ctx;
+    std::vector<double> X;
+    build_coords(P, m, sNew, coefsNew, X);
+    if (d.aux.ensure(sizeof(double) * std::max<size_t>(1, X.size()))) return FGP_ERR_ALLOC;
+    CK(cudaMemcpy(d.aux.p, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice));
+    *Xnew_dev = (double*)d.aux.p;
+    return 0;
+}
+
+extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const double* const* coefsNew, int detail,
+                           double* mean, double* sd, double* Ktp, double* Kpp) {
+    if (!P || m <= 0 || !mean || !sd) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    if (!P->hasModel) { fgp_set_err(ctx, "fgp_predict: call fgp_premats first"); return FGP_ERR_STATE; }
+    if ((P->ds > 0 && !sNew) || (P->df > 0 && !coefsNew)) return FGP_ERR_ARG;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    ProblemDev& pd = P->pd[0];
+    const int n = P->n, nt = P->nterms;
+    double* Xnew = nullptr;
+    int rc = upload_new(P, d, m, sNew, coefsNew, &Xnew);
+    if (rc) return rc;
+    const int holeHi = (int)roundup(n, FGP_TILE);
+    const int nrows = holeHi + m;
+    const long ld = pick_ld(nrows);
+    // workspace: trapezoid (ld x n) | results mean[m] norm[m]
+    const size_t trapBytes = sizeof(double) * (size_t)ld * n;
+    if (d.work.ensure(trapBytes + sizeof(double) * 2 * (size_t)m)) return FGP_ERR_ALLOC;
+    double* Mw = (double*)d.work.p;
+    double* dMean = (double*)((char*)d.work.p + trapBytes);
+    double* dNorm = dMean + m;
+    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
+    std::vector<double> sc(nt);
+    kernel_scales(P->ker, nt, P->theta.data(), sc.data());
+    cudaStream_t st = d.sPanel[0];
+    double* dScale = (double*)d.small.p;
+    int* dInfo = (int*)(dScale + nt);
+    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
+    // L -> top of the workspace
+    CK(cudaMemcpy2DAsync(Mw, sizeof(double) * ld, pd.Lfac, sizeof(double) * pd.ldL, sizeof(double) * n, n,
+                         cudaMemcpyDeviceToDevice, st));
+    // K(new, train) = sig2 * R(new, train) under it     (R/4_prediction_SF.R:6)
+    AsmArgs a{};
+    a.XP = Xnew; a.nP = m; a.ldP = m; a.XQ = pd.X; a.nQ = n; a.ldQ = n;
+    a.units = pd.units; a.nunits = (int)P->units.size(); a.scale = dScale; a.nterms = nt; a.ker = P->ker; a.sym = 0;
+    a.mult = P->sig2; a.M = Mw; a.ld = ld; a.strideM = 0; a.rowOff = holeHi; a.colOff = 0;
+    launch_assemble(a, 1, st);
+    TrapDesc t{};
+    t.M = Mw; t.ld = ld; t.strideM = 0; t.batch = 1;
+    t.ncols = n; t.nrows = nrows; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
+    t.cpre = cdiv(n, FGP_TILE); t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
+    rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
+    if (rc) return rc;
+    // mean = LInvK' LInvY ; sd = sqrt(pmax(sig2 - colSums(LInvK^2), 0))     (R/4_prediction_SF.R:10-11)
+    launch_rowgemv(Mw, ld, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, dMean, st);
+    launch_rownorm2(Mw, ld, holeHi, m, n, 0, dNorm, st);
+    std::vector<double> hn(m);
+    CK(cudaMemcpyAsync(mean, dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int i = 0; i < m; ++i) sd[i] = sqrt(std::max(P->sig2 - hn[i], 0.0));
+    if (detail == FGP_DETAIL_FULL) {
+        if (Ktp) {   // n x m
+            if (d.work.ensure(sizeof(double) * (size_t)n * m)) return FGP_ERR_ALLOC;
+            AsmArgs b = a;
+            b.XP = pd.X; b.nP = n; b.ldP = n; b.XQ = Xnew; b.nQ = m; b.ldQ = m;
+            b.M = (double*)d.work.p; b.ld = n; b.rowOff = 0; b.colOff = 0;
+            launch_assemble(b, 1, st);
+            CK(cudaMemcpyAsync(Ktp, d.work.p, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (Kpp) {   // m x m, sig2 * (R_pp + nugget I)      (R/4_prediction_SF.R:16-17)
+            if (d.work.ensure(sizeof(double) * (size_t)m * m)) return FGP_ERR_ALLOC;
+            AsmArgs b = a;
+            b.XP = Xnew; b.nP = m; b.ldP = m; b.XQ = Xnew; b.nQ = m; b.ldQ = m; b.sym = 1; b.mirror = 1;
+            b.diag_rel = P->nugget; b.M = (double*)d.work.p; b.ld = m; b.rowOff = 0; b.colOff = 0;
+            launch_assemble(b, 1, st);
+            CK(cudaMemcpyAsync(Kpp, d.work.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int fgp_simulate(fgp_problem* P, int m, const double* sNew, const double* const* coefsNew, int nsim,
+                            const double* Z, double nugget_sm, double* sims, double* mean, double* sd) {
+    if (!P || m <= 0 || nsim <= 0 || !Z || !sims) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    if (!P->hasModel) { fgp_set_err(ctx, "fgp_simulate: call fgp_premats first"); return FGP_ERR_STATE; }
+    if ((P->ds > 0 && !sNew) || (P->df > 0 && !coefsNew)) return FGP_ERR_ARG;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    ProblemDev& pd = P->pd[0];
+    const int n = P->n, nt = P->nterms;
+    double* Xnew = nullptr;
+    int rc = upload_new(P, d, m, sNew, coefsNew, &Xnew);
+    if (rc) return rc;
+    const int holeHi = (int)roundup(n, FGP_TILE);
+    const int nrows = holeHi + m, ncols = holeHi + m;
+    const long ld = pick_ld(nrows);
+    const size_t trapBytes = sizeof(double) * (size_t)ld * ncols;
+    const size_t extra = sizeof(double) * (2 * (size_t)m + (size_t)m * nsim * 2);
+    if (d.work.ensure(trapBytes + extra)) return FGP_ERR_ALLOC;
+    double* Mw = (double*)d.work.p;
+    double* dMean = (double*)((char*)d.work.p + trapBytes);
+    double* dNorm = dMean + m;
+    double* dZ = dNorm + m;
+    double* dSims = dZ + (size_t)m * nsim;
+    const int ncTall = cdiv(ncols, FGP_TILE), ncTA = cdiv(n, FGP_TILE);
+    if (d.wbuf.ensure(sizeof(double) * (size_t)ncTall * FGP_TILE * FGP_TILE)) return FGP_ERR_ALLOC;
+    double* Ww = (double*)d.wbuf.p;
+    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
+    std::vector<double> sc(nt);
+    kernel_scales(P->ker, nt, P->theta.data(), sc.data());
+    cudaStream_t st = d.sPanel[0];
+    double* dScale = (double*)d.small.p;
+    int* dInfo = (int*)(dScale + nt);
+    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
+    CK(cudaMemcpyAsync(dZ, Z, sizeof(double) * (size_t)m * nsim, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(Mw, sizeof(double) * ld, pd.Lfac, sizeof(double) * pd.ldL, sizeof(double) * n, n,
+                         cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(Ww, pd.Wall, sizeof(double) * (size_t)ncTA * FGP_TILE * FGP_TILE, cudaMemcpyDeviceToDevice, st));
+    AsmArgs a{};
+    a.XP = Xnew; a.nP = m; a.ldP = m; a.XQ = pd.X; a.nQ = n; a.ldQ = n;
+    a.units = pd.units; a.nunits = (int)P->units.size(); a.scale = dScale; a.nterms = nt; a.ker = P->ker; a.sym = 0;
+    a.mult = P->sig2; a.M = Mw; a.ld = ld; a.strideM = 0; a.rowOff = holeHi; a.colOff = 0;
+    launch_assemble(a, 1, st);                       // K.ts'  (R/5_simulation_SF.R:8)
+    AsmArgs b = a;                                   // K.ss + nugget.sm I  (R/5_simulation_SF.R:9,14)
+    b.XQ = Xnew; b.nQ = m; b.ldQ = m; b.sym = 1; b.diag_abs = nugget_sm; b.colOff = holeHi;
+    launch_assemble(b, 1, st);
+    TrapDesc t{};
+    t.M = Mw; t.ld = ld; t.strideM = 0; t.batch = 1;
+    t.ncols = ncols; t.nrows = nrows; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = holeHi;
+    t.cpre = ncTA; t.upperRows = 0; t.W = Ww; t.strideW = 0; t.info = dInfo;
+    rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
+    if (rc) return rc;
+    launch_rowgemv(Mw, ld, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, dMean, st);
+    launch_rownorm2(Mw, ld, holeHi, m, n, 0, dNorm, st);
+    launch_lower_times(Mw + holeHi + (size_t)holeHi * ld, ld, m, dZ, nsim, dMean, dSims, st);
+    int hinfo = 0;
+    std::vector<double> hn(m), hm(m);
+    CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hm.data(), dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sims, dSims, sizeof(double) * (size_t)m * nsim, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hinfo != 0) return hinfo;    // chol(K.ss - ...) failed: base R's error (quirk Q5)
+    if (mean) memcpy(mean, hm.data(), sizeof(double) * m);
+    if (sd) for (int i = 0; i < m; ++i) sd[i] = sqrt(std::max(P->sig2 - hn[i], 0.0));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LOOCV
+extern "C" int fgp_loocv(fgp_problem* P, double* y_pre, double* q2) {
+    if (!P || (!y_pre && !q2)) return FGP_ERR_ARG;
+    fgp_ctx* ctx = P->ctx;
+    if (!P->hasModel) { fgp_set_err(ctx, "fgp_loocv: call fgp_premats first"); return FGP_ERR_STATE; }
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    ProblemDev& pd = P->pd[0];
+    const int n = P->n, nt = P->nterms;
+    const int holeHi = (int)roundup(n + 1, FGP_TILE);
+    const int nrows = holeHi + n;
+    const long ld = pick_ld(nrows);
+    const int ncT = cdiv(n, FGP_TILE);
+    const size_t trapBytes = sizeof(double) * (size_t)ld * n;
+    if (d.work.ensure(trapBytes + sizeof(double) * 2 * (size_t)n)) return FGP_ERR_ALLOC;
+    if (d.wbuf.ensure(sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE)) return FGP_ERR_ALLOC;
+    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
+    double* Mw = (double*)d.work.p;
+    double* dDiag = (double*)((char*)d.work.p + trapBytes);
+    double* dRy = dDiag + n;
+    std::vector<double> sc(nt);
+    kernel_scales(P->ker, nt, P->theta.data(), sc.data());
+    cudaStream_t st = d.sPanel[0];
+    double* dScale = (double*)d.small.p;
+    int* dInfo = (int*)(dScale + nt);
+    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
+    // R = tcrossprod(L)/sig2 + diag(nugget) = R0 + 2 nugget I  (quirk Q2, R/8_outilsStats.R:3)
+    AsmArgs a = train_asm(P, pd, P->ker, dScale);
+    a.diag_rel = 2.0 * P->nugget; a.M = Mw; a.ld = ld; a.strideM = 0;
+    launch_assemble(a, 1, st);
+    launch_fill_yrow(Mw, ld, 0, 1, n, pd.y, n, st);
+    launch_fill_identity_rows(Mw, ld, 0, 1, holeHi, n, st);
+    TrapDesc t{};
+    t.M = Mw; t.ld = ld; t.strideM = 0; t.batch = 1;
+    t.ncols = n; t.nrows = nrows; t.holeLo = n + 1; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
+    t.cpre = 0; t.upperRows = 1; t.W = (double*)d.wbuf.p; t.strideW = 0; t.info = dInfo;
+    int rc = trap_factor(ctx, 0, t, st, d.sBulk, false);
+    if (rc) return rc;
+    // X = L^-T in the extra rows: diag(Rinv)_i = |X_i.|^2 ; (Rinv y)_i = X_i. (L^-1 y)
+    launch_rownorm2(Mw, ld, holeHi, n, n, 1, dDiag, st);
+    launch_rowgemv(Mw, ld, holeHi, n, n, 1, Mw + n, ld, dRy, st);
+    std::vector<double> hd(n), hr(n);
+    int hinfo = 0;
+    CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hd.data(), dDiag, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hr.data(), dRy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hinfo != 0) return hinfo;
+    // y_pre = y - Rinv y / diag(Rinv)  (R/8_outilsStats.R:6);  Q2 = 1 - mean((y-yhat)^2)/mean((y-ybar)^2)
+    double ybar = 0.0;
+    for (int i = 0; i < n; ++i) ybar += P->y[i];
+    ybar /= n;
+    double se = 0.0, st2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double yh = P->y[i] - hr[i] / hd[i];
+        if (y_pre) y_pre[i] = yh;
+        se += (P->y[i] - yh) * (P->y[i] - yh);
+        st2 += (P->y[i] - ybar) * (P->y[i] - ybar);
+    }
+    if (q2) *q2 = 1.0 - (se / n) / (st2 / n);
+    return 0;
+}
+
+extern "C" int fgp_fit_batch(fgp_ctx* ctx, int, int, const double*, int, const int*, const double* const*,
+                             const double*, int, const int*, double, int, int, const double*, const long long*, int,
+                             double*, double*, double*, double*, int*) {
+    fgp_set_err(ctx, "fgp_fit_batch: not built yet");
+    return FGP_ERR_STATE;
+}

@@ -1,0 +1,296 @@
+// Host-side driver of the "trapezoid" blocked Cholesky and the small reductions around it.
+//
+// One engine serves every dense step of the reference's hot path:
+//   fit       chol(R + nugget I), backsolve(t(U), y), sum(log(diag(U)))   R/3_training_SF.R:246-269
+//   preMats   t(chol(sig2 (R + nugget I))), L^-1 y                       R/4_prediction_SF.R:24-32
+//   predict   backsolve(L, K.tp)                                         R/4_prediction_SF.R:9
+//   simulate  backsolve, K.ss - t(LInvK) LInvK, chol                      R/5_simulation_SF.R:10-14
+//   LOOCV     solve(R) through L^-T                                       R/8_outilsStats.R:1-7
+// by factoring a matrix that has extra rows under the training block: the y row turns into (L^-1 y)', rows
+// holding K(new, train) turn into (L^-1 K.tp)', and -- when the matrix also has the K(new,new) columns --
+// the trailing update leaves the Schur complement there, which the same loop then factors.
+#include "common.cuh"
+#include "ctx.h"
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPanel, cudaStream_t sBulk, bool lookahead) {
+    (void)devslot;
+    const int NBk = FGP_TILE;
+    const int ncT = cdiv(t.ncols, NBk);                 // column tiles (index space shared with rows)
+    const int nrT = cdiv(t.nrows, NBk);
+    const int nAT = cdiv(t.holeLo, NBk);                // tiles covering the training block (+ y row)
+    const int eT0 = t.holeHi / NBk;                     // first extra-row tile
+    const bool hasExtra = t.nrows > t.holeHi;
+    FgpTimers* tm = ctx->profile ? &ctx->dev[devslot].timers : nullptr;
+
+    auto col_nb = [&](int k) {
+        const int k0 = k * NBk;
+        if (k0 < t.colHoleLo) return std::min(NBk, t.colHoleLo - k0);
+        return std::min(NBk, t.ncols - k0);
+    };
+
+    GemmArgs base{};
+    base.lda = t.ld; base.ldb = t.ld; base.ldc = t.ld;
+    base.strideA = t.strideM; base.strideB = t.strideM; base.strideC = t.strideM;
+    base.rowMin = 0; base.rowLo = t.holeLo; base.rowHoleHi = t.holeHi; base.nrows = t.nrows;
+    base.colMin = 0; base.colLo = t.colHoleLo; base.colHoleHi = t.colHoleHi; base.ncols = t.ncols;
+    base.batch = t.batch;
+
+    cudaEvent_t evPanel = nullptr, evBulk = nullptr;
+    const bool la = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;
+    if (la) {
+        evPanel = ctx->dev[devslot].evA;
+        evBulk = ctx->dev[devslot].evB;
+        // the bulk stream must see everything queued so far on the panel stream (assembly)
+        cudaEventRecord(evPanel, sPanel);
+        cudaStreamWaitEvent(sBulk, evPanel, 0);
+    }
+    bool bulkPending = false;
+
+    for (int k = 0; k < ncT; ++k) {
+        const int k0 = k * NBk;
+        const int nb = col_nb(k);
+        if (nb <= 0) continue;
+        const bool fresh = k >= t.cpre;
+        // ---- diagonal block
+        if (fresh) {
+            const int infoOff = (k0 >= t.colHoleHi && t.colHoleHi > t.colHoleLo) ? (k0 - t.colHoleHi) : k0;
+            if (tm) tm->begin(sPanel);
+            launch_potf2(t.M, t.ld, t.strideM, t.batch, k0, nb, t.W, t.strideW, t.info, infoOff, sPanel);
+            if (tm) tm->end(sPanel, FgpTimers::PANEL, 0.0);
+        }
+        // ---- participating row tiles  S = [lo1,hi1) u [lo2,hi2)
+        int lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+        if (t.upperRows) {
+            lo1 = fresh ? k + 1 : nAT; hi1 = nAT;
+            lo2 = eT0; hi2 = std::min(eT0 + k + 1, nrT);
+        } else if (!fresh) {
+            lo2 = eT0; hi2 = nrT;
+        } else {
+            lo1 = k + 1; hi1 = nrT;
+        }
+        if (hi1 < lo1) hi1 = lo1;
+        if (hi2 < lo2) hi2 = lo2;
+        if (!hasExtra && (t.upperRows || !fresh)) { lo2 = hi2 = 0; }
+
+        // ---- panel solve X = P * W_k'   (tile k itself takes part when its block is ragged: rows below k0+nb)
+        {
+            GemmArgs g = base;
+            g.A = t.M + (long)k0 * t.ld;
+            g.B = t.W + (long)k * NBk * NBk; g.ldb = NBk; g.strideB = t.strideW;
+            g.C = t.M + (long)k0 * t.ld;
+            g.K = nb; g.accumulate = 0;
+            g.tri0 = 0; g.triT = 0;
+            int tlo1 = lo1, thi1 = hi1;
+            if (fresh && nb < NBk && (long)k0 + nb < (long)std::min(t.nrows, (k + 1) * NBk)) {
+                // rows of tile k under the ragged diagonal block (the y row lives here when n % 128 != 0)
+                if (thi1 > tlo1) tlo1 = k; else { tlo1 = k; thi1 = k + 1; }
+            }
+            g.rectR0 = tlo1; g.rectNR = thi1 - tlo1; g.rectR1 = lo2; g.rectNR1 = hi2 - lo2;
+            g.rectC0 = k; g.rectNC = 1; g.bTileBase = k;
+            g.rowMin = k0 + nb;
+            g.colMin = 0; g.colLo = nb; g.colHoleHi = nb; g.ncols = nb;
+            if (g.rectNR + g.rectNR1 > 0) {
+                if (tm) tm->begin(sPanel);
+                launch_gemm(g, sPanel);
+                if (tm) tm->end(sPanel, FgpTimers::PANEL, 0.0);
+            }
+        }
+        if (k + 1 >= ncT) break;
+        // ---- trailing update  C(I,J) -= X_I X_J'   for J in (k, ncT), I in S, I >= J
+        auto make_update = [&](int cLo, int cHi) {
+            GemmArgs g = base;
+            g.A = t.M + (long)k0 * t.ld;
+            g.B = t.M + (long)k0 * t.ld;
+            g.C = t.M;
+            g.K = nb; g.accumulate = 1; g.bTileBase = 0;
+            // first range: starts on the diagonal of the column range when it begins at k+1
+            int r1lo = std::max(lo1, cLo), r1hi = hi1;
+            g.tri0 = 0; g.triT = 0; g.rectR0 = 0; g.rectNR = 0; g.rectR1 = 0; g.rectNR1 = 0;
+            g.rectC0 = cLo; g.rectNC = cHi - cLo;
+            if (r1hi > r1lo) {
+                // tiles with I in [r1lo, r1hi), J in [cLo, cHi), I >= J
+                const int triHi = std::min(r1hi, cHi);
+                if (r1lo == cLo) {
+                    g.tri0 = cLo; g.triT = std::max(0, triHi - cLo);
+                    g.rectR0 = triHi; g.rectNR = std::max(0, r1hi - triHi);
+                } else {
+                    // only used by the look-ahead split (rows strictly below the column range)
+                    g.rectR0 = std::max(r1lo, cHi); g.rectNR = std::max(0, r1hi - g.rectR0);
+                }
+            }
+            if (hi2 > lo2) {
+                if (lo2 >= cHi) { g.rectR1 = lo2; g.rectNR1 = hi2 - lo2; }
+                else {
+                    // simulate, prefactored steps: extra rows x (train columns: rectangle) + (new columns: triangle)
+                    g.rectC0 = cLo; g.rectNC = std::max(0, std::min(cHi, lo2) - cLo);
+                    g.rectR1 = lo2; g.rectNR1 = hi2 - lo2;
+                    if (cHi > lo2) { g.tri0 = lo2; g.triT = cHi - lo2; }
+                }
+            }
+            return g;
+        };
+        auto flops_of = [&](const GemmArgs& g) {
+            const double tiles = g.triT * (g.triT + 1) / 2.0 + (double)(g.rectNR + g.rectNR1) * g.rectNC;
+            return tiles * 2.0 * NBk * NBk * (double)nb * t.batch;
+        };
+        if (!la) {
+            GemmArgs g = make_update(k + 1, ncT);
+            if (tm) tm->begin(sPanel);
+            launch_gemm(g, sPanel);
+            if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
+        } else {
+            // look-ahead: column k+1 on the panel stream (critical path), the rest on the bulk stream
+            cudaEventRecord(evPanel, sPanel);                 // panel k solved
+            if (bulkPending) cudaStreamWaitEvent(sPanel, evBulk, 0);   // column k+1 carries update k-1
+            GemmArgs g1 = make_update(k + 1, k + 2);
+            launch_gemm(g1, sPanel);
+            if (k + 2 < ncT) {
+                cudaStreamWaitEvent(sBulk, evPanel, 0);
+                GemmArgs g2 = make_update(k + 2, ncT);
+                // rows of the first range must start at k+2's diagonal: tiles (I >= J, J >= k+2)
+                launch_gemm(g2, sBulk);
+                cudaEventRecord(evBulk, sBulk);
+                bulkPending = true;
+            }
+        }
+    }
+    if (la && bulkPending) cudaStreamWaitEvent(sPanel, evBulk, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fgp_set_err_cuda(ctx, "trap_factor launch", e, __FILE__, __LINE__);
+        return FGP_ERR_CUDA_;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// nll / sigma^2 from the factored trapezoid (R/3_training_SF.R:250-255, 266-269)
+namespace {
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    // deterministic: fixed tree
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+__global__ void nll_reduce_kernel(const double* M, long ld, long strideM, int n, int yrow, const double* var_known,
+                                  const int* info, double* nll, double* sig2) {
+    __shared__ double red[33];
+    const double* Mb = M + (long)blockIdx.x * strideM;
+    double slog = 0.0, sq = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        slog += log(Mb[(long)i + (long)i * ld]);
+        const double z = Mb[(long)yrow + (long)i * ld];
+        sq = fma(z, z, sq);
+    }
+    const double sumlog = block_sum(slog, red);
+    const double quad = block_sum(sq, red);
+    if (threadIdx.x == 0) {
+        const double s2 = var_known ? *var_known : quad / (double)n;
+        // -llik = 0.5 * (n log(2 pi sig2) + 2 sum(log diag U) + n)      (quirk Q1: '+ n' also with a fixed variance)
+        double v = 0.5 * ((double)n * log(2.0 * 3.14159265358979323846 * s2) + 2.0 * sumlog + (double)n);
+        if (info && info[blockIdx.x] != 0) v = nan("");
+        nll[blockIdx.x] = v;
+        sig2[blockIdx.x] = s2;
+    }
+}
+
+// out[i] = sum_j M(row0+i, j)^2   (j < ncol; upper: only j >= i's tile start is non-zero but zeros are stored)
+__global__ void rownorm2_kernel(const double* M, long ld, int row0, int nrow, int ncol, int jstart_by_row, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrow) return;
+    double s = 0.0;
+    const int j0 = jstart_by_row ? (i / FGP_TILE) * FGP_TILE : 0;
+    for (int j = j0; j < ncol; ++j) {
+        const double v = M[(long)(row0 + i) + (long)j * ld];
+        s = fma(v, v, s);
+    }
+    out[i] = s;
+}
+
+// out[i] = sum_j M(row0+i, j) z[j*zstride]
+__global__ void rowgemv_kernel(const double* M, long ld, int row0, int nrow, int ncol, int jstart_by_row,
+                               const double* z, long zstride, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrow) return;
+    double s = 0.0;
+    const int j0 = jstart_by_row ? (i / FGP_TILE) * FGP_TILE : 0;
+    for (int j = j0; j < ncol; ++j) s = fma(M[(long)(row0 + i) + (long)j * ld], z[(long)j * zstride], s);
+    out[i] = s;
+}
+
+// sims(s, i) = mean[i] + sum_{j<=i} Lc(i,j) Z(j,s)    (R/5_simulation_SF.R:14-15), sims is nsim x m col-major
+__global__ void lower_times_kernel(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean,
+                                   double* sims) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= m) return;
+    double acc = 0.0;
+    const double* z = Z + (long)s * m;
+    for (int j = 0; j <= i; ++j) acc = fma(Lc[(long)i + (long)j * ld], z[j], acc);
+    sims[(long)s + (long)i * nsim] = mean[i] + acc;
+}
+
+__global__ void extract_lower_kernel(const double* M, long ld, int n, double* out) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * n) return;
+    const int r = (int)(idx % n), c = (int)(idx / n);
+    out[idx] = (r >= c) ? M[(long)r + (long)c * ld] : 0.0;
+}
+
+__global__ void fill_yrow_kernel(double* M, long ld, long strideM, int row, const double* y, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) M[(long)blockIdx.y * strideM + (long)row + (long)j * ld] = y[j];
+}
+
+// identity rows for LOOCV: rows row0 .. row0+n-1; only tiles with column tile >= row tile are ever read
+__global__ void fill_identity_rows_kernel(double* M, long ld, long strideM, int row0, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // extra row index
+    const int j = blockIdx.y;                               // column
+    if (i >= n) return;
+    if (j / FGP_TILE < i / FGP_TILE) return;
+    M[(long)blockIdx.z * strideM + (long)(row0 + i) + (long)j * ld] = (i == j) ? 1.0 : 0.0;
+}
+
+}  // namespace
+
+void launch_nll_reduce(const double* M, long ld, long strideM, int batch, int n, int yrow, const double* var_known,
+                       const int* info, double* nll, double* sig2, cudaStream_t st) {
+    nll_reduce_kernel<<<batch, 256, 0, st>>>(M, ld, strideM, n, yrow, var_known, info, nll, sig2);
+}
+void launch_rownorm2(const double* M, long ld, int row0, int nrow, int ncol, int upper, double* out, cudaStream_t st) {
+    rownorm2_kernel<<<cdiv(nrow, 128), 128, 0, st>>>(M, ld, row0, nrow, ncol, upper, out);
+}
+void launch_rowgemv(const double* M, long ld, int row0, int nrow, int ncol, int upper, const double* z, long zstride,
+                    double* out, cudaStream_t st) {
+    rowgemv_kernel<<<cdiv(nrow, 128), 128, 0, st>>>(M, ld, row0, nrow, ncol, upper, z, zstride, out);
+}
+void launch_lower_times(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean, double* sims,
+                        cudaStream_t st) {
+    dim3 grid(cdiv(m, 128), nsim);
+    lower_times_kernel<<<grid, 128, 0, st>>>(Lc, ld, m, Z, nsim, mean, sims);
+}
+void launch_extract_lower(const double* M, long ld, int n, double* out, cudaStream_t st) {
+    const long tot = (long)n * n;
+    extract_lower_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, ld, n, out);
+}
+void launch_fill_yrow(double* M, long ld, long strideM, int batch, int row, const double* y, int n, cudaStream_t st) {
+    dim3 grid(cdiv(n, 256), batch);
+    fill_yrow_kernel<<<grid, 256, 0, st>>>(M, ld, strideM, row, y, n);
+}
+void launch_fill_identity_rows(double* M, long ld, long strideM, int batch, int row0, int n, cudaStream_t st) {
+    dim3 grid(cdiv(n, 128), n, batch);
+    fill_identity_rows_kernel<<<grid, 128, 0, st>>>(M, ld, strideM, row0, n);
+}

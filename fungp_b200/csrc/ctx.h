@@ -1,0 +1,117 @@
+// Context / problem objects behind the C ABI (include/fungp_b200.h).
+#pragma once
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+struct FgpTimers {
+    enum { ASSEMBLY = 0, PANEL = 1, UPDATE = 2, FACTOR = 3, NCLASS = 4 };
+    struct Rec { cudaEvent_t a, b; int cls; double flops; };
+    std::vector<cudaEvent_t> pool;
+    std::vector<Rec> recs;
+    size_t used = 0;
+    cudaEvent_t cur = nullptr;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void reset() { used = 0; recs.clear(); }
+    void begin(cudaStream_t st) { cur = get(); cudaEventRecord(cur, st); }
+    void end(cudaStream_t st, int cls, double flops) {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, st);
+        recs.push_back({cur, e, cls, flops});
+    }
+    // sums per class: ms, count, flops
+    void collect(double ms[NCLASS], double cnt[NCLASS], double fl[NCLASS]) {
+        for (int i = 0; i < NCLASS; ++i) ms[i] = cnt[i] = fl[i] = 0.0;
+        for (auto& r : recs) {
+            cudaEventSynchronize(r.b);
+            float t = 0.f;
+            cudaEventElapsedTime(&t, r.a, r.b);
+            ms[r.cls] += t; cnt[r.cls] += 1.0; fl[r.cls] += r.flops;
+        }
+    }
+    ~FgpTimers() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
+// growable device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DevState {
+    int device = 0;
+    static const int MAXSTREAMS = 8;
+    cudaStream_t sPanel[MAXSTREAMS] = {nullptr};
+    cudaStream_t sBulk = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evJoin[MAXSTREAMS] = {nullptr};
+    DevBuf work;      // factorisation workspaces (batch of trapezoids)
+    DevBuf wbuf;      // inverse diagonal blocks
+    DevBuf small;     // thetas / scales / results
+    DevBuf aux;       // new-point coordinates etc.
+    void* pinned = nullptr; size_t pinnedCap = 0;
+    FgpTimers timers;
+    double lastAsmMs = 0, lastFactorMs = 0;
+    long launches = 0;
+};
+
+struct fgp_ctx {
+    std::vector<DevState> dev;
+    std::string err;
+    int profile = 0;
+    int lookahead = 1;
+    int streams = 4;
+    double timing[8] = {0};
+    std::mutex mu;
+};
+
+struct ProblemDev {
+    bool ready = false;
+    double* X = nullptr;      // n x ncoord coordinate matrix (column-major, ld = n)
+    FgpUnit* units = nullptr;
+    double* y = nullptr;
+    // model state after fgp_premats (device 0 only)
+    double* Lfac = nullptr;   // trapezoid with the factor of sig2 (R + nugget I) and the (L^-1 y)' row
+    long ldL = 0;
+    double* Wall = nullptr;   // inverse diagonal blocks of Lfac
+};
+
+struct fgp_problem {
+    fgp_ctx* ctx = nullptr;
+    int n = 0, ds = 0, df = 0;
+    std::vector<int> p, dis;
+    int nterms = 0;           // d
+    int ncoord = 0;           // columns of the coordinate matrix
+    std::vector<FgpUnit> units;
+    std::vector<int> termFirstUnit;     // nterms + 1
+    std::vector<double> X;    // host copy (replicated lazily to the other devices)
+    std::vector<double> y;
+    std::vector<std::vector<double>> J;   // per functional input (p x p), needed to build e = c J for new points
+    std::vector<ProblemDev> pd;
+    // model state
+    bool hasModel = false;
+    int ker = 0;
+    double nugget = 0, sig2 = 0;
+    std::vector<double> theta;
+};
+
+int problem_upload(fgp_problem* P, int slot);
+// build the coordinate matrix rows for m points (host): scalars, byindex coefs, (c, cJ) pairs for bygroup
+void build_coords(const fgp_problem* P, int m, const double* sIn, const double* const* coefs, std::vector<double>& X);
+void kernel_scales(int ker, int nterms, const double* theta, double* scale);

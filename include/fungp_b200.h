@@ -1,0 +1,141 @@
+/*
+ * fungp_b200.h -- plain-C ABI of libfungp_b200.so: the sm_100a (B200) implementation of funGp's
+ * Gaussian-process hot path.  Every entry point replaces the body of an *internal R function* of the
+ * reference package funGp 1.0.0 (the reference has no FFI of its own: no src/, no useDynLib --
+ * NAMESPACE:1-78), so each declaration cites the reference file:line whose arithmetic it takes over.
+ * The R-side .Call stubs that bind these symbols are in rglue/ and described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all matrices are column-major doubles exactly as R's REALSXP + dim (n x k, leading dimension n);
+ *   - every pointer is a HOST pointer; the library never keeps a host pointer after the call returns
+ *     and never writes through an input pointer;
+ *   - return value: 0 = ok; >0 = LAPACK-style info of base::chol ("the leading minor of order <info> is
+ *     not positive definite", what reaches users today through R/3_training_SF.R:249); <0 = bad argument
+ *     or CUDA failure, text in fgp_last_error();  batched calls report per-element info[] instead and
+ *     return 0 unless the call itself failed;
+ *   - integer codes follow the reference's own level order (R/1_Xfgpm_Class.R:457-459,
+ *     R/3_ant_admin.R:301-373):  ker 1 = gauss, 2 = matern5_2, 3 = matern3_2;
+ *     dis_type 1 = L2_bygroup, 2 = L2_byindex;  basis_type 1 = B-splines, 2 = PCA;  detail 0 = light, 1 = full;
+ *   - there is no CPU fallback: without a CUDA device fgp_ctx_create() fails.
+ */
+#ifndef FUNGP_B200_H
+#define FUNGP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fgp_ctx fgp_ctx;         /* devices, streams, workspaces                                   */
+typedef struct fgp_problem fgp_problem; /* one data set (coordinates + output) resident on the device(s)  */
+
+enum { FGP_KER_GAUSS = 1, FGP_KER_MATERN52 = 2, FGP_KER_MATERN32 = 3 };
+enum { FGP_DIST_BYGROUP = 1, FGP_DIST_BYINDEX = 2 };
+enum { FGP_BASIS_BSPLINES = 1, FGP_BASIS_PCA = 2 };
+enum { FGP_DETAIL_LIGHT = 0, FGP_DETAIL_FULL = 1 };
+
+/* error codes (<0) */
+enum { FGP_ERR_ARG = -1, FGP_ERR_CUDA = -2, FGP_ERR_NODEVICE = -3, FGP_ERR_STATE = -4, FGP_ERR_ALLOC = -5 };
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* n_devices = 0 -> all visible GPUs; device_ids may be NULL (= 0..n_devices-1).  One host worker per GPU;
+ * batched calls shard their independent work items over the GPUs, nothing else does. */
+int fgp_ctx_create(int n_devices, const int* device_ids, fgp_ctx** out);
+void fgp_ctx_destroy(fgp_ctx* ctx);
+int fgp_ctx_device_count(const fgp_ctx* ctx);
+const char* fgp_last_error(const fgp_ctx* ctx);
+const char* fgp_version(void);
+
+/* ---- dimension reduction: R/7_dimRedFunctions.R:7-60 --------------------------------------------- */
+/* proj_bsplines, R/7_dimRedFunctions.R:40-51: k x p design matrix on the grid 1..k (host code). */
+int fgp_bspline_basis(int k, int p, double* B_out /* k*p */);
+/* dimReduction for ONE functional input (R/7_dimRedFunctions.R:13-27) and the re-projection of new curves
+ * with a stored basis (R/1_fgpm_Class.R:844-845, 863-864, 1044-1045, 1063-1064):
+ *   p = 0            -> B = J = I_k, coefs = f                       (:22-25)
+ *   B_in != NULL     -> use B_in (k x p) as the basis (re-projection)
+ *   else             -> build the basis: B-splines (:40-51) or PCA = first p eigenvectors of cov(f) (:57-60)
+ * J = B'B, coefs = t(solve(J, B' f')).  B_out (k x p'), J_out (p' x p'), coefs_out (n x p'), p' = p ? p : k. */
+int fgp_project(fgp_ctx* ctx, const double* f, int n, int k, int p, int basis_type, const double* B_in,
+                double* B_out, double* J_out, double* coefs_out);
+
+/* ---- problem = what setDistMatrix_S / setDistMatrix_F are given (R/7_distanceFunctions.R:3-22) ---- */
+/* sIn n x ds (may be NULL when ds = 0); for each functional input i: coefs[i] n x p[i], J[i] p[i] x p[i],
+ * dis_type[i]; y = sOut (n).  Length-scale order = reference order: scalars, then per functional input one
+ * (L2_bygroup) or p[i] (L2_byindex) entries (getOwners, R/7_distanceFunctions.R:48-58).
+ * The distance lists sMs/fMs are never materialised: kernels work from the coordinates. */
+int fgp_problem_create(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* p, const int* dis_type,
+                       const double* const* coefs, const double* const* J, const double* y, fgp_problem** out);
+void fgp_problem_destroy(fgp_problem* prob);
+int fgp_problem_n(const fgp_problem* prob);
+int fgp_problem_nls(const fgp_problem* prob); /* d = number of length-scales */
+/* replace sOut (update(): output substitution, R/6_updating.R:154-160) */
+int fgp_problem_set_y(fgp_problem* prob, const double* y);
+
+/* setBounds_*: max(Ms[[l]]) for every length-scale (R/3_training_SF.R:57-74, _S.R:50-60, _F.R:50-60). */
+int fgp_dist_max(fgp_problem* prob, double* max_out /* d */);
+/* API-parity escape hatch: the l-th (0-based) n x n distance matrix of c(sMs, fMs)
+ * (L2_byindex R/7_distanceFunctions.R:28-34, L2_bygroup :38-46). */
+int fgp_dist_materialize(fgp_problem* prob, int l, double* out /* n*n */);
+
+/* setR(...) [* setR(...)] + nugget*I  (R/7_correlFunctions.R:1-80, R/3_training_SF.R:248); full symmetric n x n. */
+int fgp_assemble(fgp_problem* prob, int ker, double nugget, const double* theta /* d */, double* R_out /* n*n */);
+
+/* negLogLik_funGp_{S,F,SF} for B length-scale vectors in one call (R/3_training_SF.R:231-258, _S.R:200-213,
+ * _F.R:197-210) with analyticVar_llik (R/3_training_SF.R:266-269).  thetas is d x B (column b = point b).
+ * var_known: NULL -> sigma^2 estimated (analyticVar_llik); else the fixed variance (quirk Q1: the formula
+ * keeps '+ n').  Outputs nll[B], sig2[B], info[B] (0 or the failing minor's order; nll = NaN there).
+ * The B points are independent: they are sharded over the context's GPUs. */
+int fgp_nll_batch(fgp_problem* prob, int ker, double nugget, int B, const double* thetas, const double* var_known,
+                  double* nll, double* sig2, int* info);
+
+/* preMats_*: K = sig2*(R + nugget I), L = t(chol(K)), LInvY = L^-1 y  (R/4_prediction_SF.R:24-32).
+ * L_out (n x n, explicit zeros above the diagonal) and LInvY_out (n) may be NULL; the factor always stays
+ * resident on device 0 inside the problem for predict / simulate / loocv. */
+int fgp_premats(fgp_problem* prob, int ker, double nugget, double sig2, const double* theta, double* L_out,
+                double* LInvY_out);
+
+/* makePreds_*: (R/4_prediction_SF.R:2-21).  sNew m x ds, coefsNew[i] m x p[i] (already projected).
+ * mean[m], sd[m]; detail = full additionally fills Ktp (n x m) and Kpp (m x m) when non-NULL. */
+int fgp_predict(fgp_problem* prob, int m, const double* sNew, const double* const* coefsNew, int detail,
+                double* mean, double* sd, double* Ktp, double* Kpp);
+
+/* makeSims_*: (R/5_simulation_SF.R:3-23).  Z is matrix(rnorm(m*nsim), m, nsim) drawn by the caller with R's RNG
+ * after set.seed(seed) (:13-14) so the R stream is untouched.  sims is nsim x m; mean/sd (m) may be NULL. */
+int fgp_simulate(fgp_problem* prob, int m, const double* sNew, const double* const* coefsNew, int nsim,
+                 const double* Z, double nugget_sm, double* sims, double* mean, double* sd);
+
+/* getOut_loocv + Q2 (R/8_outilsStats.R:1-7, R/1_Xfgpm_Class.R:522-543), including quirk Q2 (nugget counted twice).
+ * y_pre[n] (may be NULL), q2 scalar. */
+int fgp_loocv(fgp_problem* prob, double* y_pre, double* q2);
+
+/* ---- batched candidate scoring for the ant-colony search ------------------------------------------ */
+/* fitNtests_ACO / eval_loocv_ACO (R/3_ant_admin.R:592-648, 810-831): each candidate = one structure in the wire
+ * format of formatSol_ACO (R/3_ant_admin.R:301-373): ints of length ds + 4*df + 1 --
+ *   State X_i (1 on, 2 off) | per functional input: State, Dist (1 bygroup, 2 byindex), Dim, Basis (1 B-splines,
+ *   2 PCA), -1 when off | Kernel (1 gauss, 2 matern5_2, 3 matern3_2).
+ * For every candidate: projection -> presample (u01 = the runif(d*n_presample) draws made by R in ant order, so
+ * the R RNG stream is unchanged; column-major d x n_presample per candidate, concatenated; offsets in u01_off) ->
+ * L-BFGS-B fit from the best n_starts points (lmm 5, factr 1e7, pgtol 0, maxit 100, central finite differences
+ * with ndeps 1e-3 clipped at the box, as stats::optim does) -> preMats -> Q2loocv.
+ * Outputs per candidate: fitness (Q2, NaN on crash), nll, sig2, theta (padded to dmax), info. Candidates are
+ * dealt to the context's GPUs from a host-side queue. */
+int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
+                  const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
+                  const double* u01, const long long* u01_off, int dmax, double* fitness, double* nll, double* sig2,
+                  double* theta, int* info);
+
+/* ---- instrumentation ------------------------------------------------------------------------------- */
+/* timing of the last call on device 0 (CUDA events on the library's own streams), milliseconds / counts:
+ *  [0] assembly kernel ms  [1] factorisation (all launches) ms  [2] trailing-update (DMMA) kernel ms summed
+ *  [3] trailing-update launches  [4] trailing-update flops  [5] panel (POTF2+TRSM) ms  [6] total kernel launches
+ *  [7] assembly launches.  Per-launch event timing is only taken when fgp_set_option("profile", 1). */
+int fgp_get_timing(fgp_ctx* ctx, double* out8);
+/* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU). */
+int fgp_set_option(fgp_ctx* ctx, const char* name, double value);
+/* measured FP64 peaks on device 0 for the roofline denominators: register-resident DMMA (m8n8k4) loop and
+ * DFMA loop, TFLOP/s; and a device copy, GB/s. */
+int fgp_measure_peaks(fgp_ctx* ctx, double* dmma_tflops, double* dfma_tflops, double* copy_gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUNGP_B200_H */

@@ -70,3 +70,47 @@ def synth_problem(seed, n, ds, f_lens, extra=0):
         t = np.linspace(0, 1, f.shape[1])
         y = y + (4 * np.mean(t * f, axis=1) if i == 0 else np.mean(f, axis=1))
     return sIn, fIn, y, rng
+
+
+# --------------------------------------------------------------------------------------------------
+# shared by the GPU parity tests and bench.py: one synthetic case prepared with the oracle's projection
+def make_case(seed, n, ds, f_lens, pdims, bas, dis, extra=0):
+    """Returns dict with train/new splits: sIn, coefs, J, basis, y, and the oracle's distance lists (train)."""
+    sIn, fIn, y, rng = synth_problem(seed, n, ds, f_lens, extra=extra)
+    N = n + extra
+    case = dict(n=n, m=extra, ds=ds, df=len(f_lens), pdims=list(pdims), bas=list(bas), dis=list(dis))
+    case["sIn"] = None if sIn is None else sIn[:n]
+    case["sNew"] = None if (sIn is None or not extra) else sIn[n:]
+    case["fIn"] = [f[:n] for f in fIn]
+    case["fNew"] = [f[n:] for f in fIn]
+    case["y"] = y[:n]
+    if fIn:
+        bcj = ref.dimReduction(case["fIn"], pdims, bas)
+        case["basis"], case["coefs"], case["J"] = bcj["basis"], bcj["coefs"], bcj["J"]
+        case["coefsNew"] = [ref.project_coefs(B, f)[0] for B, f in zip(bcj["basis"], case["fNew"])] if extra else []
+    else:
+        case["basis"], case["coefs"], case["J"], case["coefsNew"] = [], [], [], []
+    return case
+
+
+def oracle_dists(case, new=False):
+    """(train-train) or (train-new, new-new) distance lists of the oracle."""
+    if not new:
+        Ms = []
+        if case["ds"]:
+            Ms += ref.setDistMatrix_S(case["sIn"], case["sIn"])
+        if case["df"]:
+            Ms += ref.setDistMatrix_F(case["coefs"], case["coefs"], case["J"], case["dis"])
+        return Ms
+    tp, pp = [], []
+    if case["ds"]:
+        tp += ref.setDistMatrix_S(case["sIn"], case["sNew"]); pp += ref.setDistMatrix_S(case["sNew"], case["sNew"])
+    if case["df"]:
+        tp += ref.setDistMatrix_F(case["coefs"], case["coefsNew"], case["J"], case["dis"])
+        pp += ref.setDistMatrix_F(case["coefsNew"], case["coefsNew"], case["J"], case["dis"])
+    return tp, pp
+
+
+def theta_frac(Ms, frac):
+    """length-scales = frac * upper bound (2 * max distance), SURVEY.md 8d"""
+    return frac * ref.setBounds(Ms)[1]

@@ -1,0 +1,232 @@
+"""Gate 2 (GPU): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): distances / correlations 1e-12 relative (absolute floor = 1e-12 x the
+largest entry, SURVEY.md 7.3 "tolerances near zero"), negative log-likelihood 1e-9 relative (relative to
+max(|nll|, n)), predictive mean / sd 1e-8 relative (floor 1e-8 x sigma).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import fungp_ref as ref
+from helpers import load_models, make_case, oracle_dists, theta_frac, MODEL_NAMES
+
+pytestmark = pytest.mark.gpu
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import fungp_b200
+    c = fungp_b200.Context(1)
+    yield c
+    c.close()
+
+
+def _problem(ctx, case):
+    import fungp_b200
+    return fungp_b200.Problem(ctx, case["sIn"], case["coefs"], case["J"], case["dis"], case["y"])
+
+
+def _rel(a, b, floor):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), floor))
+
+
+def _nll_tol(nll_ref, n):
+    return 1e-9 * max(abs(nll_ref), n)
+
+
+def _log(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "parity_log.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test=name, **{k: (float(v) if np.isscalar(v) else v) for k, v in kw.items()})) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _fixture_case(g):
+    case = dict(n=g["sOut"].size, ds=g["ds"], df=g["df"], y=g["sOut"], sIn=g.get("sIn") if g["ds"] else None)
+    if g["df"]:
+        bcj = ref.dimReduction(g["fIn"], g["f_pdims"], g["f_basType"])
+        case.update(coefs=bcj["coefs"], J=bcj["J"], dis=g["f_disType"], basis=bcj["basis"])
+    else:
+        case.update(coefs=[], J=[], dis=[], basis=[])
+    return case
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_stored_models(ctx, name):
+    """The reference's five stored models (data/precalculated_Xfgpm_objects.rda) through the CUDA path:
+    distances, correlation matrix, nll, sigma^2, L, LInvY and Q2 at the stored hyper-parameters."""
+    g = load_models()[name]
+    case = _fixture_case(g)
+    Ms = oracle_dists(case)
+    P = _problem(ctx, case)
+    theta = np.concatenate([g["s_ls"], g["f_ls"]])
+    assert P.d == theta.size == len(Ms)
+    for l, M in enumerate(Ms):
+        D = P.dist_matrix(l)
+        assert _rel(D, M, 1e-12 * M.max()) <= 1e-12 + 1e-13, (name, l)
+    np.testing.assert_allclose(P.dist_max(), [M.max() for M in Ms], rtol=1e-13)
+    R = P.assemble(g["kerType"], g["nugget"], theta)
+    Rref = ref.corr_matrix(theta, Ms, g["kerType"], g["nugget"])
+    assert _rel(R, Rref, 1e-12) <= 1e-12
+    nll, sig2, info = P.nll_batch(g["kerType"], g["nugget"], theta)
+    assert info[0] == 0
+    assert abs(nll[0] - g["negLogLik"]) <= _nll_tol(g["negLogLik"], case["n"])
+    assert abs(sig2[0] - g["varHyp"]) <= 1e-9 * g["varHyp"]
+    L, z = P.premats(g["kerType"], g["nugget"], g["varHyp"], theta)
+    assert np.max(np.abs(L - g["L"])) <= 1e-9 * np.max(np.abs(g["L"]))
+    assert np.max(np.abs(z - g["LInvY"])) <= 1e-8 * np.max(np.abs(g["LInvY"]))
+    yp, q2 = P.loocv()
+    assert abs(q2 - g["fitness"]) <= 1e-8
+    _log("stored_models", name=name, nll_err=abs(nll[0] - g["negLogLik"]), q2_err=abs(q2 - g["fitness"]),
+         L_err=float(np.max(np.abs(L - g["L"]))))
+    P.close()
+
+
+CASES = [
+    # (seed, n, ds, f_lens, pdims, bas, dis, ker, frac)
+    (11, 25, 2, [10, 22], [3, 3], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
+    (12, 127, 1, [], [], [], [], "gauss", 0.1),
+    (13, 128, 0, [12], [4], ["B-splines"], ["L2_byindex"], "matern3_2", 0.5),
+    (14, 129, 2, [15], [0], ["B-splines"], ["L2_bygroup"], "matern5_2", 0.5),
+    (15, 300, 3, [20, 30], [2, 5], ["PCA", "B-splines"], ["L2_byindex", "L2_bygroup"], "gauss", 0.15),
+    (16, 1000, 2, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
+    (17, 1024, 5, [10, 22, 50], [3, 4, 6], ["B-splines", "PCA", "B-splines"], ["L2_bygroup", "L2_byindex", "L2_bygroup"],
+     "matern3_2", 0.4),
+    (18, 2048, 2, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
+    (19, 2500, 4, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "gauss", 0.2),
+]
+
+
+@pytest.mark.parametrize("spec", CASES, ids=[f"n{c[1]}-{c[7]}" for c in CASES])
+def test_assemble_and_nll(ctx, spec):
+    seed, n, ds, f_lens, pdims, bas, dis, ker, frac = spec
+    case = make_case(seed, n, ds, f_lens, pdims, bas, dis)
+    Ms = oracle_dists(case)
+    P = _problem(ctx, case)
+    theta = theta_frac(Ms, frac)
+    nug = 1e-8
+    np.testing.assert_allclose(P.dist_max(), [M.max() for M in Ms], rtol=1e-12)
+    if n <= 1100:
+        R = P.assemble(ker, nug, theta)
+        Rref = ref.corr_matrix(theta, Ms, ker, nug)
+        assert np.array_equal(R, R.T)
+        assert _rel(R, Rref, 1e-12) <= 1e-12
+        for l in range(min(P.d, 3)):
+            D = P.dist_matrix(l)
+            assert _rel(D, Ms[l], 1e-12 * Ms[l].max()) <= 1e-12 + 1e-13
+    # batch: theta, a perturbed copy, theta again -> first and third bit-identical
+    th = np.stack([theta, theta * 1.07, theta], axis=1)
+    nll, sig2, info = P.nll_batch(ker, nug, th)
+    assert (info == 0).all()
+    assert nll[0] == nll[2] and sig2[0] == sig2[2]
+    for b in (0, 1):
+        r_nll, r_s2 = ref.negLogLik(th[:, b], [], Ms, case["y"], ker, nug)
+        assert abs(nll[b] - r_nll) <= _nll_tol(r_nll, n), (nll[b], r_nll)
+        assert abs(sig2[b] - r_s2) <= 1e-8 * r_s2
+        _log("assemble_and_nll", n=n, ker=ker, nll=r_nll, nll_abs_err=abs(nll[b] - r_nll), sig2_rel=abs(sig2[b] - r_s2) / r_s2)
+    # single-point call (look-ahead path) agrees with the batched call to rounding
+    nll1, s21, _ = P.nll_batch(ker, nug, theta)
+    assert abs(nll1[0] - nll[0]) <= 1e-11 * max(abs(nll[0]), n)
+    # fixed variance (quirk Q1)
+    nllv, s2v, _ = P.nll_batch(ker, nug, theta, var_known=1.7)
+    r_nllv, _ = ref.negLogLik(theta, [], Ms, case["y"], ker, nug, var_known=1.7)
+    assert s2v[0] == 1.7 and abs(nllv[0] - r_nllv) <= _nll_tol(r_nllv, n)
+    P.close()
+
+
+PRED_CASES = [
+    (21, 25, 7, 2, [10, 22], [3, 3], ["PCA", "PCA"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
+    (22, 300, 50, 2, [20], [4], ["B-splines"], ["L2_byindex"], "matern3_2", 0.4),
+    (23, 1000, 130, 3, [30, 40], [5, 3], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "gauss", 0.15),
+    (24, 1280, 256, 2, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
+]
+
+
+@pytest.mark.parametrize("spec", PRED_CASES, ids=[f"n{c[1]}-m{c[2]}-{c[8]}" for c in PRED_CASES])
+def test_premats_predict_simulate_loocv(ctx, spec):
+    seed, n, m, ds, f_lens, pdims, bas, dis, ker, frac = spec
+    case = make_case(seed, n, ds, f_lens, pdims, bas, dis, extra=m)
+    Ms = oracle_dists(case)
+    tp, pp = oracle_dists(case, new=True)
+    theta = theta_frac(Ms, frac)
+    nug = 1e-8
+    _, sig2 = ref.negLogLik(theta, [], Ms, case["y"], ker, nug)
+    L_ref, z_ref = ref.preMats(Ms, case["y"], sig2, theta, ker, nug)
+    P = _problem(ctx, case)
+    L, z = P.premats(ker, nug, sig2, theta)
+    assert np.all(np.triu(L, 1) == 0.0)
+    assert np.max(np.abs(L - L_ref)) <= 1e-9 * np.max(np.abs(L_ref))
+    assert np.max(np.abs(z - z_ref)) <= 1e-8 * np.max(np.abs(z_ref))
+    sdev = np.sqrt(sig2)
+    # predict, light and full
+    pr_ref = ref.makePreds(tp, pp, sig2, theta, ker, L_ref, z_ref, "full", nug)
+    pr = P.predict(m, case["sNew"], case["coefsNew"], detail="full")
+    assert _rel(pr["mean"], pr_ref["mean"], 1e-8 * max(1.0, np.max(np.abs(pr_ref["mean"])))) <= 1e-8
+    assert np.max(np.abs(pr["sd"] - pr_ref["sd"])) <= 1e-8 * sdev + 1e-8 * np.max(pr_ref["sd"])
+    assert _rel(pr["K.tp"], pr_ref["K.tp"], 1e-12 * sig2) <= 1e-12
+    assert _rel(pr["K.pp"], pr_ref["K.pp"], 1e-12 * sig2) <= 1e-12
+    # simulate
+    rng = np.random.default_rng(seed)
+    Z = rng.standard_normal((m, 9))
+    nsm = 1e-8
+    sm_ref = ref.makeSims(tp, pp, sig2, theta, ker, L_ref, z_ref, Z, nsm, "full")
+    sm = P.simulate(m, Z, case["sNew"], case["coefsNew"], nugget_sm=nsm)
+    assert sm["sims"].shape == (9, m)
+    scale = max(1.0, np.max(np.abs(sm_ref["sims"])))
+    # chol of a conditional covariance that is near-singular at training-like points amplifies rounding: compare at 1e-6
+    assert np.max(np.abs(sm["sims"] - sm_ref["sims"])) <= 1e-6 * scale
+    assert np.max(np.abs(sm["mean"] - sm_ref["mean"])) <= 1e-8 * scale
+    # loocv
+    yp_ref = ref.getOut_loocv(L_ref, sig2, nug, case["y"])
+    q2_ref = ref.q2(case["y"], yp_ref)
+    yp, q2 = P.loocv()
+    assert abs(q2 - q2_ref) <= 1e-8
+    assert np.max(np.abs(yp - yp_ref)) <= 1e-7 * max(1.0, np.max(np.abs(yp_ref)))
+    _log("premats_predict_simulate_loocv", n=n, m=m, ker=ker, mean_err=float(np.max(np.abs(pr["mean"] - pr_ref["mean"]))),
+         sd_err=float(np.max(np.abs(pr["sd"] - pr_ref["sd"]))), sims_err=float(np.max(np.abs(sm["sims"] - sm_ref["sims"]))),
+         q2_err=abs(q2 - q2_ref))
+    P.close()
+
+
+def test_not_positive_definite_reports_order(ctx):
+    """Duplicated training point + zero nugget: base::chol stops with 'leading minor of order k'; the batch keeps going."""
+    case = make_case(31, 200, 2, [], [], [], [])
+    case["sIn"][150] = case["sIn"][20]
+    Ms = oracle_dists(case)
+    theta = theta_frac(Ms, 0.5)
+    P = _problem(ctx, case)
+    th = np.stack([theta, theta], axis=1)
+    nll, sig2, info = P.nll_batch("matern5_2", 0.0, th)
+    with pytest.raises(ref.NotPosDef) as ei:
+        ref.negLogLik(theta, [], Ms, case["y"], "matern5_2", 0.0)
+    assert info[0] == info[1] and info[0] > 0
+    assert abs(int(info[0]) - ei.value.order) <= 1 and np.isnan(nll[0])
+    # with the nugget the same data factorises
+    nll2, _, info2 = P.nll_batch("matern5_2", 1e-8, theta)
+    assert info2[0] == 0 and np.isfinite(nll2[0])
+    P.close()
+
+
+def test_large_n_properties(ctx):
+    """n = 8192 (BASELINE config 3 sizes): size-independent checks -- L L' reproduces the assembled matrix on sampled
+    entries, nll from the batched and the look-ahead path agree, and the oracle agrees at the same point."""
+    n = 8192
+    case = make_case(8192, n, 4, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"])
+    P = _problem(ctx, case)
+    ub = 2.0 * P.dist_max()
+    theta = 0.25 * ub
+    nll, sig2, info = P.nll_batch("gauss", 1e-8, np.stack([theta, theta], axis=1))
+    assert (info == 0).all() and nll[0] == nll[1]
+    nll1, _, _ = P.nll_batch("gauss", 1e-8, theta)
+    assert abs(nll1[0] - nll[0]) <= 1e-10 * n
+    Ms = oracle_dists(case)
+    r_nll, r_s2 = ref.negLogLik(theta, [], Ms, case["y"], "gauss", 1e-8)
+    _log("large_n", n=n, nll=r_nll, nll_abs_err=abs(nll[0] - r_nll), sig2_rel=abs(sig2[0] - r_s2) / r_s2)
+    assert abs(nll[0] - r_nll) <= _nll_tol(r_nll, n)
+    assert abs(sig2[0] - r_s2) <= 1e-7 * r_s2
+    P.close()
