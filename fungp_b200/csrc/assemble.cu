@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int gi = i0 + lr[2 * h];
-            if (gi + 1 < a.nP && (((a.rowOff + gi) & 1) == 0)) {
+            if (gi + 1 < a.nP && ((reinterpret_cast<uintptr_t>(colp + gi) & 15) == 0)) {
                 *reinterpret_cast<double2*>(colp + gi) = make_double2(v[2 * h], v[2 * h + 1]);
             } else {
                 if (gi < a.nP) colp[gi] = v[2 * h];

@@ -39,10 +39,10 @@ def _nll_tol(nll_ref, n):
     return 1e-9 * max(abs(nll_ref), n)
 
 
-def _log(name, **kw):
+def _log(test, **kw):
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "parity_log.jsonl"), "a") as f:
-        f.write(json.dumps(dict(test=name, **{k: (float(v) if np.isscalar(v) else v) for k, v in kw.items()})) + "\n")
+        f.write(json.dumps(dict(test=test, **{k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else v) for k, v in kw.items()})) + "\n")
 
 
 # ------------------------------------------------------------------------------------------------------------
