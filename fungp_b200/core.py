@@ -4,6 +4,7 @@ Everything numeric happens in libfungp_b200.so on the GPU; these classes only ma
 float64 arrays (R's layout) in and out.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -54,9 +55,12 @@ class Context:
         if rc != 0:
             raise FgpError(f"fgp_ctx_create failed ({rc}): no sm_100 CUDA device visible -- fungp_b200 has no CPU path")
         self.h = h
+        self._problems = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "h", None):
+            for p in list(self._problems):   # problems hold a pointer to the context: release them first
+                p.close()
             self.lib.fgp_ctx_destroy(self.h)
             self.h = None
 
@@ -83,7 +87,7 @@ class Context:
         out = np.zeros(8)
         self.check(self.lib.fgp_get_timing(self.h, _dp(out)), "fgp_get_timing")
         return dict(assembly_ms=out[0], factor_ms=out[1], update_ms=out[2], update_launches=int(out[3]),
-                    update_flops=out[4], panel_ms=out[5], launches=int(out[6]), assembly_launches=int(out[7]))
+                    update_flops=out[4], potf2_ms=out[5], trsm_ms=out[6], launches=int(out[7]))
 
     def measure_peaks(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
@@ -135,10 +139,12 @@ class Problem:
         self.d = lib.fgp_problem_nls(h)
         self.ds, self.df = ds, df
         self._keep = (s, coefs, J, y)
+        ctx._problems.add(self)
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.fgp_problem_destroy(self.h)
+            if getattr(self.ctx, "h", None):
+                self.ctx.lib.fgp_problem_destroy(self.h)
             self.h = None
 
     def __del__(self):

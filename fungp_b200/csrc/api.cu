@@ -101,6 +101,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     if (!ctx || !name) return FGP_ERR_ARG;
     if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
+    else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "streams")) ctx->streams = std::max(1, std::min((int)value, (int)DevState::MAXSTREAMS));
     else { fgp_set_err(ctx, std::string("unknown option ") + name); return FGP_ERR_ARG; }
     return 0;
@@ -118,8 +119,8 @@ extern "C" int fgp_get_timing(fgp_ctx* ctx, double* out8) {
     out8[3] = cnt[FgpTimers::UPDATE];
     out8[4] = fl[FgpTimers::UPDATE];
     out8[5] = ms[FgpTimers::PANEL];
-    out8[6] = cnt[FgpTimers::UPDATE] + cnt[FgpTimers::PANEL] + cnt[FgpTimers::ASSEMBLY];
-    out8[7] = cnt[FgpTimers::ASSEMBLY];
+    out8[6] = ms[FgpTimers::TRSM];
+    out8[7] = cnt[FgpTimers::UPDATE] + cnt[FgpTimers::PANEL] + cnt[FgpTimers::TRSM] + cnt[FgpTimers::ASSEMBLY];
     return 0;
 }
 

@@ -14,15 +14,25 @@
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Two-level right-looking schedule.  Column tiles (128 wide) are grouped into outer panels of `outer` tiles:
+//   inside a panel   potf2(k) -> panel solve(k) -> update of the panel's remaining columns (K = 128)
+//   after the panel  one trailing update of everything to the right with K = outer*128
+// The wide K is what keeps the DMMA pipe busy: every 128x128 C tile is read and written once per 2*128*128*K
+// flops, and with one CTA per SM that traffic is not overlapped with the MMAs (measured: K = 128 -> 53 % of the
+// DMMA peak in the update kernel).  With look-ahead the next panel's columns are updated first on the (high
+// priority) panel stream so that its factorisation overlaps the rest of the trailing update on the bulk stream.
 int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPanel, cudaStream_t sBulk, bool lookahead) {
-    (void)devslot;
     const int NBk = FGP_TILE;
     const int ncT = cdiv(t.ncols, NBk);                 // column tiles (index space shared with rows)
     const int nrT = cdiv(t.nrows, NBk);
     const int nAT = cdiv(t.holeLo, NBk);                // tiles covering the training block (+ y row)
     const int eT0 = t.holeHi / NBk;                     // first extra-row tile
     const bool hasExtra = t.nrows > t.holeHi;
+    const bool colHole = t.colHoleHi > t.colHoleLo || (t.colHoleLo < t.ncols);
+    const int colSegTile = (t.colHoleLo < t.ncols) ? t.colHoleHi / NBk : ncT;   // first tile of the second column segment
     FgpTimers* tm = ctx->profile ? &ctx->dev[devslot].timers : nullptr;
+    const int outer = std::max(1, ctx->outer);
+    (void)colHole;
 
     auto col_nb = [&](int k) {
         const int k0 = k * NBk;
@@ -48,113 +58,135 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     }
     bool bulkPending = false;
 
-    for (int k = 0; k < ncT; ++k) {
-        const int k0 = k * NBk;
-        const int nb = col_nb(k);
-        if (nb <= 0) continue;
+    // participating row tiles of step k:  S = [lo1,hi1) u [lo2,hi2)
+    struct RowSet { int lo1, hi1, lo2, hi2; };
+    auto rows_of = [&](int k) {
         const bool fresh = k >= t.cpre;
-        // ---- diagonal block
-        if (fresh) {
-            const int infoOff = (k0 >= t.colHoleHi && t.colHoleHi > t.colHoleLo) ? (k0 - t.colHoleHi) : k0;
-            if (tm) tm->begin(sPanel);
-            launch_potf2(t.M, t.ld, t.strideM, t.batch, k0, nb, t.W, t.strideW, t.info, infoOff, sPanel);
-            if (tm) tm->end(sPanel, FgpTimers::PANEL, 0.0);
-        }
-        // ---- participating row tiles  S = [lo1,hi1) u [lo2,hi2)
-        int lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+        RowSet r{0, 0, 0, 0};
         if (t.upperRows) {
-            lo1 = fresh ? k + 1 : nAT; hi1 = nAT;
-            lo2 = eT0; hi2 = std::min(eT0 + k + 1, nrT);
+            r.lo1 = fresh ? k + 1 : nAT; r.hi1 = nAT;
+            r.lo2 = eT0; r.hi2 = std::min(eT0 + k + 1, nrT);
         } else if (!fresh) {
-            lo2 = eT0; hi2 = nrT;
+            r.lo2 = eT0; r.hi2 = nrT;
         } else {
-            lo1 = k + 1; hi1 = nrT;
+            r.lo1 = k + 1; r.hi1 = nrT;
         }
-        if (hi1 < lo1) hi1 = lo1;
-        if (hi2 < lo2) hi2 = lo2;
-        if (!hasExtra && (t.upperRows || !fresh)) { lo2 = hi2 = 0; }
-
-        // ---- panel solve X = P * W_k'   (tile k itself takes part when its block is ragged: rows below k0+nb)
-        {
-            GemmArgs g = base;
-            g.A = t.M + (long)k0 * t.ld;
-            g.B = t.W + (long)k * NBk * NBk; g.ldb = NBk; g.strideB = t.strideW;
-            g.C = t.M + (long)k0 * t.ld;
-            g.K = nb; g.accumulate = 0;
-            g.tri0 = 0; g.triT = 0;
-            int tlo1 = lo1, thi1 = hi1;
-            if (fresh && nb < NBk && (long)k0 + nb < (long)std::min(t.nrows, (k + 1) * NBk)) {
-                // rows of tile k under the ragged diagonal block (the y row lives here when n % 128 != 0)
-                if (thi1 > tlo1) tlo1 = k; else { tlo1 = k; thi1 = k + 1; }
+        if (r.hi1 < r.lo1) r.hi1 = r.lo1;
+        if (r.hi2 < r.lo2) r.hi2 = r.lo2;
+        if (!hasExtra && (t.upperRows || !fresh)) { r.lo2 = r.hi2 = 0; }
+        return r;
+    };
+    // C(I,J) -= X_I X_J'  for J in [cLo,cHi), I in S, I >= J;  X = columns [kA*128, kA*128+K)
+    auto make_update = [&](int kA, int K, const RowSet& S, int cLo, int cHi) {
+        GemmArgs g = base;
+        g.A = t.M + (long)kA * NBk * t.ld;
+        g.B = g.A;
+        g.C = t.M;
+        g.K = K; g.accumulate = 1; g.bTileBase = 0;
+        g.tri0 = 0; g.triT = 0; g.rectR0 = 0; g.rectNR = 0; g.rectR1 = 0; g.rectNR1 = 0;
+        g.rectC0 = cLo; g.rectNC = cHi - cLo;
+        const int r1lo = std::max(S.lo1, cLo), r1hi = S.hi1;
+        if (r1hi > r1lo) {
+            const int triHi = std::min(r1hi, cHi);
+            if (r1lo == cLo) {
+                g.tri0 = cLo; g.triT = std::max(0, triHi - cLo);
+                g.rectR0 = triHi; g.rectNR = std::max(0, r1hi - triHi);
+            } else {
+                g.rectR0 = std::max(r1lo, cHi); g.rectNR = std::max(0, r1hi - g.rectR0);
             }
-            g.rectR0 = tlo1; g.rectNR = thi1 - tlo1; g.rectR1 = lo2; g.rectNR1 = hi2 - lo2;
-            g.rectC0 = k; g.rectNC = 1; g.bTileBase = k;
-            g.rowMin = k0 + nb;
-            g.colMin = 0; g.colLo = nb; g.colHoleHi = nb; g.ncols = nb;
-            if (g.rectNR + g.rectNR1 > 0) {
+        }
+        if (S.hi2 > S.lo2) {
+            if (S.lo2 >= cHi) { g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2; }
+            else {
+                // simulate, prefactored steps: extra rows x (train columns: rectangle) + (new columns: triangle)
+                g.rectNC = std::max(0, std::min(cHi, S.lo2) - cLo);
+                g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2;
+                if (cHi > S.lo2) { g.tri0 = std::max(S.lo2, cLo); g.triT = cHi - g.tri0; }
+            }
+        }
+        return g;
+    };
+    auto flops_of = [&](const GemmArgs& g) {
+        const double tiles = g.triT * (g.triT + 1) / 2.0 + (double)(g.rectNR + g.rectNR1) * g.rectNC;
+        return tiles * 2.0 * NBk * NBk * (double)g.K * t.batch;
+    };
+
+    int k = 0;
+    while (k < ncT) {
+        // ---- outer panel [k, kend): never straddles the prefactored boundary or the column hole
+        int kend = std::min(k + outer, ncT);
+        if (k < t.cpre) kend = std::min(kend, t.cpre);
+        if (k < colSegTile) kend = std::min(kend, colSegTile);
+        int Kpanel = 0;
+        for (int kk = k; kk < kend; ++kk) {
+            const int k0 = kk * NBk;
+            const int nb = col_nb(kk);
+            if (nb <= 0) continue;
+            Kpanel += nb;
+            const bool fresh = kk >= t.cpre;
+            // -- diagonal block
+            if (fresh) {
+                const int infoOff = (k0 >= t.colHoleHi && t.colHoleLo < t.ncols) ? (k0 - t.colHoleHi) : k0;
                 if (tm) tm->begin(sPanel);
-                launch_gemm(g, sPanel);
+                launch_potf2(t.M, t.ld, t.strideM, t.batch, k0, nb, t.W, t.strideW, t.info, infoOff, sPanel);
                 if (tm) tm->end(sPanel, FgpTimers::PANEL, 0.0);
             }
-        }
-        if (k + 1 >= ncT) break;
-        // ---- trailing update  C(I,J) -= X_I X_J'   for J in (k, ncT), I in S, I >= J
-        auto make_update = [&](int cLo, int cHi) {
-            GemmArgs g = base;
-            g.A = t.M + (long)k0 * t.ld;
-            g.B = t.M + (long)k0 * t.ld;
-            g.C = t.M;
-            g.K = nb; g.accumulate = 1; g.bTileBase = 0;
-            // first range: starts on the diagonal of the column range when it begins at k+1
-            int r1lo = std::max(lo1, cLo), r1hi = hi1;
-            g.tri0 = 0; g.triT = 0; g.rectR0 = 0; g.rectNR = 0; g.rectR1 = 0; g.rectNR1 = 0;
-            g.rectC0 = cLo; g.rectNC = cHi - cLo;
-            if (r1hi > r1lo) {
-                // tiles with I in [r1lo, r1hi), J in [cLo, cHi), I >= J
-                const int triHi = std::min(r1hi, cHi);
-                if (r1lo == cLo) {
-                    g.tri0 = cLo; g.triT = std::max(0, triHi - cLo);
-                    g.rectR0 = triHi; g.rectNR = std::max(0, r1hi - triHi);
-                } else {
-                    // only used by the look-ahead split (rows strictly below the column range)
-                    g.rectR0 = std::max(r1lo, cHi); g.rectNR = std::max(0, r1hi - g.rectR0);
+            const RowSet S = rows_of(kk);
+            // -- panel solve X = P * W_k'  (tile kk itself takes part when its block is ragged: rows below k0+nb)
+            {
+                GemmArgs g = base;
+                g.A = t.M + (long)k0 * t.ld;
+                g.B = t.W + (long)kk * NBk * NBk; g.ldb = NBk; g.strideB = t.strideW;
+                g.C = t.M + (long)k0 * t.ld;
+                g.K = nb; g.accumulate = 0;
+                g.tri0 = 0; g.triT = 0;
+                int tlo1 = S.lo1, thi1 = S.hi1;
+                if (fresh && nb < NBk && (long)k0 + nb < (long)std::min(t.nrows, (kk + 1) * NBk)) {
+                    if (thi1 > tlo1) tlo1 = kk; else { tlo1 = kk; thi1 = kk + 1; }
+                }
+                g.rectR0 = tlo1; g.rectNR = thi1 - tlo1; g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2;
+                g.rectC0 = kk; g.rectNC = 1; g.bTileBase = kk;
+                g.rowMin = k0 + nb;
+                g.colMin = 0; g.colLo = nb; g.colHoleHi = nb; g.ncols = nb;
+                if (g.rectNR + g.rectNR1 > 0) {
+                    if (tm) tm->begin(sPanel);
+                    launch_gemm(g, sPanel);
+                    if (tm) tm->end(sPanel, FgpTimers::TRSM, 0.0);
                 }
             }
-            if (hi2 > lo2) {
-                if (lo2 >= cHi) { g.rectR1 = lo2; g.rectNR1 = hi2 - lo2; }
-                else {
-                    // simulate, prefactored steps: extra rows x (train columns: rectangle) + (new columns: triangle)
-                    g.rectC0 = cLo; g.rectNC = std::max(0, std::min(cHi, lo2) - cLo);
-                    g.rectR1 = lo2; g.rectNR1 = hi2 - lo2;
-                    if (cHi > lo2) { g.tri0 = lo2; g.triT = cHi - lo2; }
-                }
-            }
-            return g;
-        };
-        auto flops_of = [&](const GemmArgs& g) {
-            const double tiles = g.triT * (g.triT + 1) / 2.0 + (double)(g.rectNR + g.rectNR1) * g.rectNC;
-            return tiles * 2.0 * NBk * NBk * (double)nb * t.batch;
-        };
-        if (!la) {
-            GemmArgs g = make_update(k + 1, ncT);
-            if (tm) tm->begin(sPanel);
-            launch_gemm(g, sPanel);
-            if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
-        } else {
-            // look-ahead: column k+1 on the panel stream (critical path), the rest on the bulk stream
-            cudaEventRecord(evPanel, sPanel);                 // panel k solved
-            if (bulkPending) cudaStreamWaitEvent(sPanel, evBulk, 0);   // column k+1 carries update k-1
-            GemmArgs g1 = make_update(k + 1, k + 2);
-            launch_gemm(g1, sPanel);
-            if (k + 2 < ncT) {
-                cudaStreamWaitEvent(sBulk, evPanel, 0);
-                GemmArgs g2 = make_update(k + 2, ncT);
-                // rows of the first range must start at k+2's diagonal: tiles (I >= J, J >= k+2)
-                launch_gemm(g2, sBulk);
-                cudaEventRecord(evBulk, sBulk);
-                bulkPending = true;
+            // -- update of the panel's remaining columns
+            if (kk + 1 < kend) {
+                GemmArgs g = make_update(kk, nb, S, kk + 1, kend);
+                if (tm) tm->begin(sPanel);
+                launch_gemm(g, sPanel);
+                if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
             }
         }
+        // ---- trailing update with the whole panel
+        if (kend < ncT && Kpanel > 0) {
+            const RowSet S = rows_of(kend - 1);
+            if (!la) {
+                GemmArgs g = make_update(k, Kpanel, S, kend, ncT);
+                if (tm) tm->begin(sPanel);
+                launch_gemm(g, sPanel);
+                if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
+            } else {
+                // look-ahead: the next panel's columns on the panel stream (critical path), the rest on the bulk stream
+                int kend2 = std::min(kend + outer, ncT);
+                if (kend < t.cpre) kend2 = std::min(kend2, t.cpre);
+                if (kend < colSegTile) kend2 = std::min(kend2, colSegTile);
+                cudaEventRecord(evPanel, sPanel);                           // panel solved
+                if (bulkPending) cudaStreamWaitEvent(sPanel, evBulk, 0);   // its columns carry the previous bulk update
+                launch_gemm(make_update(k, Kpanel, S, kend, kend2), sPanel);
+                if (kend2 < ncT) {
+                    cudaStreamWaitEvent(sBulk, evPanel, 0);
+                    launch_gemm(make_update(k, Kpanel, S, kend2, ncT), sBulk);
+                    cudaEventRecord(evBulk, sBulk);
+                    bulkPending = true;
+                }
+            }
+        }
+        k = kend;
     }
     if (la && bulkPending) cudaStreamWaitEvent(sPanel, evBulk, 0);
     cudaError_t e = cudaGetLastError();
@@ -255,12 +287,12 @@ __global__ void fill_yrow_kernel(double* M, long ld, long strideM, int row, cons
     if (j < n) M[(long)blockIdx.y * strideM + (long)row + (long)j * ld] = y[j];
 }
 
-// identity rows for LOOCV: rows row0 .. row0+n-1; only tiles with column tile >= row tile are ever read
+// identity rows for LOOCV: rows row0 .. row0+n-1 (all columns: the wide trailing update reads rows that have not
+// started yet and needs zeros there)
 __global__ void fill_identity_rows_kernel(double* M, long ld, long strideM, int row0, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // extra row index
     const int j = blockIdx.y;                               // column
     if (i >= n) return;
-    if (j / FGP_TILE < i / FGP_TILE) return;
     M[(long)blockIdx.z * strideM + (long)(row0 + i) + (long)j * ld] = (i == j) ? 1.0 : 0.0;
 }
 

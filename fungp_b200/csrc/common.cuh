@@ -110,6 +110,7 @@ struct GemmArgs {
     int rowMin, rowLo, rowHoleHi, nrows;       // valid r: r >= rowMin && (r < rowLo || (rowHoleHi <= r < nrows))
     int colMin, colLo, colHoleHi, ncols;       // same for c
     int batch;
+    int dbg;                                   // experiment switches, honoured only when built with -DFGP_GEMM_DEBUG
 };
 void launch_gemm(const GemmArgs& g, cudaStream_t st);
 

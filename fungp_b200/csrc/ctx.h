@@ -6,7 +6,7 @@
 #include <memory>
 
 struct FgpTimers {
-    enum { ASSEMBLY = 0, PANEL = 1, UPDATE = 2, FACTOR = 3, NCLASS = 4 };
+    enum { ASSEMBLY = 0, PANEL = 1, UPDATE = 2, FACTOR = 3, TRSM = 4, NCLASS = 5 };
     struct Rec { cudaEvent_t a, b; int cls; double flops; };
     std::vector<cudaEvent_t> pool;
     std::vector<Rec> recs;
@@ -77,6 +77,7 @@ struct fgp_ctx {
     int profile = 0;
     int lookahead = 1;
     int streams = 4;
+    int outer = 4;            // column tiles per outer panel (trailing update K = outer*128)
     double timing[8] = {0};
     std::mutex mu;
 };

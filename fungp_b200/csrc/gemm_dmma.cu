@@ -12,6 +12,12 @@
 // conflict-free 256-byte LDS.64, 3-stage pipeline over K chunks of 32.
 #include "common.cuh"
 
+#ifdef FGP_GEMM_DEBUG
+#define DBG(bit) (g.dbg & (bit))
+#else
+#define DBG(bit) 0
+#endif
+
 namespace {
 
 constexpr int KC = 32;                      // k extent of one pipeline stage
@@ -21,8 +27,12 @@ constexpr int STAGE = 2 * OPER;             // A + B
 constexpr int GEMM_SMEM = STAGES * STAGE * 8;
 constexpr int GEMM_THREADS = 256;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes));
+// all-or-nothing 16-byte copy: zero-fill when `ignore` (a variable src-size makes ptxas emit a long branchy
+// sequence per copy -- measured: it halved the kernel's throughput)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ignore) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n cp.async.cg.shared.global [%0], [%1], 16, p;\n}\n" ::"r"(dst),
+        "l"(src), "r"((int)ignore));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -38,26 +48,50 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 struct Valid {
     int mn, lo, holeHi, n;
     __device__ __forceinline__ bool operator()(int r) const { return r >= mn && (r < lo || (r >= holeHi && r < n)); }
-    // bytes to copy for the even-aligned pair (r, r+1).  (invalid, valid) copies both: the first element exists in
-    // memory (r+1 does) and only feeds an output row/column that is never stored.
-    __device__ __forceinline__ int pair_bytes(int r) const { return (*this)(r + 1) ? 16 : ((*this)(r) ? 8 : 0); }
 };
 
-// stage one 128 x KC operand chunk: global (col-major, rows contiguous) -> smem [rb 16][k KC][8]
-__device__ __forceinline__ void load_operand(double* sm, const double* g, long ld, int row0, int k0, int K,
-                                             const Valid& v, int tid) {
+// Shared-memory operand layout, per stage: [row block of 8: 16][k group of 4: KC/4][32 doubles], the 32 doubles of
+// one (8 rows x 4 k) fragment ordered [row>>2][k&3][row&3].  A DMMA fragment load (lane -> row lane>>2, k lane&3) then
+// reads 32 distinct consecutive doubles split 16 + 16 between the half-warps: conflict-free LDS.64.
+__device__ __forceinline__ int frag_lane_off(int lane) { return (lane >> 4) * 16 + (lane & 3) * 4 + ((lane >> 2) & 3); }
+
+// Per-thread copy plan for one operand: 8 pieces of 16 bytes (2 rows x 1 k) per K chunk.
+// piece i: row block rb = (tid>>7) + 2i, rows 2*(tid&3) + {0,1}, k = (tid>>2)&31
+struct CopyPlan {
+    const double* gptr;   // global address of (row0 + (tid>>7)*8 + 2*(tid&3), k = kq); + i*16 rows, + kc*ld per chunk
+    uint32_t sdst;        // shared byte offset inside an operand slab for piece 0; + i*(2*8*32*8) bytes
+    unsigned okmask;      // bit i: the row pair of piece i has at least one valid row
+    int kq;
+};
+__device__ __forceinline__ CopyPlan make_plan(const double* g, long ld, int row0, const Valid& v, int tid) {
+    CopyPlan p;
     const int r2 = tid & 3;
-    const int kq = (tid >> 2) & 31;
-    const int k = k0 + kq;
-    const bool kok = k < K;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
+    p.kq = (tid >> 2) & 31;
+    const int rloc = (tid >> 7) * 8 + 2 * r2;
+    p.gptr = g + row0 + rloc + (long)p.kq * ld;
+    const int r = 2 * r2;
+    p.sdst = (uint32_t)(((((tid >> 7) * (KC / 4) + (p.kq >> 2)) * 32) + (r >> 2) * 16 + (p.kq & 3) * 4 + (r & 3)) * 8);
+    p.okmask = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int rb = (tid >> 7) + 2 * i;
-        const int row = row0 + rb * 8 + 2 * r2;
-        int bytes = kok ? v.pair_bytes(row) : 0;
-        const double* src = bytes ? (g + row + (long)k * ld) : g;
-        cp_async16(sbase + (uint32_t)(((rb * KC + kq) * 8 + 2 * r2) * 8), src, bytes);
+        const int row = row0 + rloc + 16 * i;
+        // (invalid, valid) / (valid, invalid) pairs are copied whole: the partner row exists in memory (ld is padded)
+        // and only feeds an output row / column that is never stored
+        if (v(row) || v(row + 1)) p.okmask |= 1u << i;
+    }
+    return p;
+}
+__device__ __forceinline__ void issue_piece(const CopyPlan& p, uint32_t slab, const double* src, bool kok, int i) {
+    const bool ok = kok && ((p.okmask >> i) & 1u);
+    cp_async16(slab + p.sdst + (uint32_t)(i * 2 * (KC / 4) * 32 * 8), ok ? (const void*)(src + 16 * i) : (const void*)p.gptr, !ok);
+}
+__device__ __forceinline__ void issue_copy(const CopyPlan& p, uint32_t slab, long ld, int k0, int K) {
+    const bool kok = (k0 + p.kq) < K;
+    const double* src = p.gptr + (long)k0 * ld;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool ok = kok && ((p.okmask >> i) & 1u);
+        cp_async16(slab + p.sdst + (uint32_t)(i * 2 * (KC / 4) * 32 * 8), ok ? (const void*)(src + 16 * i) : (const void*)p.gptr, !ok);
     }
 }
 
@@ -95,15 +129,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g) 
     const int colBase = (J - g.bTileBase) * FGP_TILE;
     const Valid rv{g.rowMin, g.rowLo, g.rowHoleHi, g.nrows};
     const Valid cv{g.colMin, g.colLo, g.colHoleHi, g.ncols};
-
     const int nchunks = (g.K + KC - 1) / KC;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+
+    const CopyPlan pa = make_plan(A, g.lda, rowBase, rv, tid);
+    const CopyPlan pb = make_plan(B, g.ldb, colBase, cv, tid);
 
     // ---- prologue: first STAGES-1 chunks in flight
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nchunks) {
-            load_operand(smem + s * STAGE, A, g.lda, rowBase, s * KC, g.K, rv, tid);
-            load_operand(smem + s * STAGE + OPER, B, g.ldb, colBase, s * KC, g.K, cv, tid);
+            issue_copy(pa, sbase + (uint32_t)(s * STAGE * 8), g.lda, s * KC, g.K);
+            issue_copy(pb, sbase + (uint32_t)((s * STAGE + OPER) * 8), g.ldb, s * KC, g.K);
         }
         cp_async_commit();
     }
@@ -128,6 +165,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g) 
     // diagonal tile of the symmetric update: warps entirely above the diagonal do nothing
     if (g.accumulate && inTri && I == J && (wm * 32 + 31 < wn * 64)) active = false;
     if (!active) rmask = 0;
+    const bool full = __all_sync(0xffffffffu, rmask == 0xFu && cmask == 0xFFFFu);
+    double* Cw = C + (long)(wrow + r_lane) + (long)(wcol + c_lane) * g.ldc;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -135,70 +174,95 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g) 
             acc[mi][ni][0] = 0.0;
             acc[mi][ni][1] = 0.0;
         }
-    if (g.accumulate && active) {
+    if (g.accumulate && active && !DBG(1)) {
+        if (full) {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const long r = wrow + mi * 8 + r_lane;
+            for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
-                const long c = wcol + ni * 8 + c_lane;
-                if ((rmask >> mi) & 1u) {
-                    if ((cmask >> (2 * ni)) & 1u) acc[mi][ni][0] = C[r + c * g.ldc];
-                    if ((cmask >> (2 * ni + 1)) & 1u) acc[mi][ni][1] = C[r + (c + 1) * g.ldc];
+                for (int mi = 0; mi < 4; ++mi) {
+                    acc[mi][ni][0] = Cw[mi * 8 + (long)(ni * 8) * g.ldc];
+                    acc[mi][ni][1] = Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc];
                 }
-            }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const bool rok = (rmask >> mi) & 1u;
+                    if (rok && ((cmask >> (2 * ni)) & 1u)) acc[mi][ni][0] = Cw[mi * 8 + (long)(ni * 8) * g.ldc];
+                    if (rok && ((cmask >> (2 * ni + 1)) & 1u)) acc[mi][ni][1] = Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc];
+                }
         }
     }
 
     // ---- main loop over K chunks
-    const int fragoff = (lane & 3) * 8 + (lane >> 2);   // (k%4, row%8) position inside a [k][8] slab
+    const int fragoff = frag_lane_off(lane);
+    const int sgnmask = g.accumulate ? (int)0x80000000 : 0;   // C -= A B': flip the sign bit of the A fragments (integer op)
     for (int c = 0; c < nchunks; ++c) {
         cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            const int cn = c + STAGES - 1;
-            if (cn < nchunks) {
-                double* st = smem + (cn % STAGES) * STAGE;
-                load_operand(st, A, g.lda, rowBase, cn * KC, g.K, rv, tid);
-                load_operand(st + OPER, B, g.ldb, colBase, cn * KC, g.K, cv, tid);
-            }
-            cp_async_commit();
-        }
-        if (active) {
-            const double* As = smem + (c % STAGES) * STAGE + (wm * 4) * KC * 8 + fragoff;
-            const double* Bs = smem + (c % STAGES) * STAGE + OPER + (wn * 8) * KC * 8 + fragoff;
+        if (!DBG(8)) __syncthreads();
+        // the copies of chunk c+STAGES-1 are spread over the 8 k-steps below (one 16-byte piece of A and of B per
+        // step and thread) instead of being issued in one burst after the barrier: a burst keeps every warp in the
+        // LSU queue while the DMMA pipe drains (measured: -15 % at K = 512)
+        const int cn = c + STAGES - 1;
+        const bool doCopy = (cn < nchunks) && !DBG(4);
+        const uint32_t stA = sbase + (uint32_t)((cn % STAGES) * STAGE * 8);
+        const uint32_t stB = stA + OPER * 8;
+        const bool kokA = (cn * KC + pa.kq) < g.K, kokB = (cn * KC + pb.kq) < g.K;
+        const double* srcA = pa.gptr + (long)(cn * KC) * g.lda;
+        const double* srcB = pb.gptr + (long)(cn * KC) * g.ldb;
+        if (active && !DBG(16)) {
+            const double* As = smem + (c % STAGES) * STAGE + (wm * 4) * (KC / 4) * 32 + fragoff;
+            const double* Bs = smem + (c % STAGES) * STAGE + OPER + (wn * 8) * (KC / 4) * 32 + fragoff;
 #pragma unroll
             for (int kk = 0; kk < KC / 4; ++kk) {
                 double a[4], bb[8];
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * KC * 8 + kk * 32];
+                for (int mi = 0; mi < 4; ++mi) {
+                    const double v = As[(mi * (KC / 4) + kk) * 32];
+                    a[mi] = __hiloint2double(__double2hiint(v) ^ sgnmask, __double2loint(v));
+                }
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[ni * KC * 8 + kk * 32];
-                if (g.accumulate) {
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) a[mi] = -a[mi];
+                for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[(ni * (KC / 4) + kk) * 32];
+                if (doCopy) {
+                    issue_piece(pa, stA, srcA, kokA, kk);
+                    issue_piece(pb, stB, srcB, kokB, kk);
                 }
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
             }
+        } else if (doCopy) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                issue_piece(pa, stA, srcA, kokA, i);
+                issue_piece(pb, stB, srcB, kokB, i);
+            }
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
     // ---- epilogue
-    if (active) {
+    if (active && !DBG(2)) {
+        if (full) {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const long r = wrow + mi * 8 + r_lane;
-            if (!((rmask >> mi) & 1u)) continue;
+            for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
-                const long c = wcol + ni * 8 + c_lane;
-                if ((cmask >> (2 * ni)) & 1u) C[r + c * g.ldc] = acc[mi][ni][0];
-                if ((cmask >> (2 * ni + 1)) & 1u) C[r + (c + 1) * g.ldc] = acc[mi][ni][1];
-            }
+                for (int mi = 0; mi < 4; ++mi) {
+                    Cw[mi * 8 + (long)(ni * 8) * g.ldc] = acc[mi][ni][0];
+                    Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc] = acc[mi][ni][1];
+                }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const bool rok = (rmask >> mi) & 1u;
+                    if (rok && ((cmask >> (2 * ni)) & 1u)) Cw[mi * 8 + (long)(ni * 8) * g.ldc] = acc[mi][ni][0];
+                    if (rok && ((cmask >> (2 * ni + 1)) & 1u)) Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc] = acc[mi][ni][1];
+                }
         }
     }
 }

@@ -19,6 +19,16 @@ constexpr int SB = 32;
 constexpr int POTF2_THREADS = 256;
 constexpr int POTF2_SMEM = (NB * LDT + NB * SB + SB + NB) * 8;
 
+// 1/sqrt(d) for the pivots: MUFU seed (rsqrt.approx, ~2^-20 relative) + one cubically convergent correction, all
+// FMA.  This sits on the factorisation's only truly serial chain (one pivot per column), so its latency -- not its
+// throughput -- is what matters; the libdevice rsqrt() is ~2x longer.  Result within ~1 ulp.
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d * y, y, 1.0);                 // 1 - d y^2
+    return fma(y * e, fma(0.375, e, 0.5), y);             // y (1 + e/2 + 3 e^2/8)
+}
+
 template <bool FACTOR>
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, int ncolsValid, double* W,
@@ -50,6 +60,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, i
     }
 
     // ---- load: lower triangle of the block, identity padding, zeros above the diagonal
+#pragma unroll 16
     for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
         const int r = idx & (NB - 1), c = idx >> 7;
         double v = 0.0;
@@ -66,24 +77,34 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, i
         // ---- (a) factor the 32x32 diagonal sub-block (warp 0), or just invert its diagonal
         if (warp == 0) {
             if (FACTOR) {
+                // lane = row.  Two dependency chains per column, both kept in registers / shuffles:
+                //   pivots:  dg (this lane's own diagonal entry, updated with -l^2 every column) -> shfl -> rsqrt
+                //   column:  a[j+1] gets its last update from a shuffle of l, not from shared memory
+                // the remaining updates a[c], c > j+1, read column j back from shared memory (broadcast) off-chain.
                 double a[SB];
 #pragma unroll
                 for (int j = 0; j < SB; ++j) a[j] = T[(o + j) * LDT + o + lane];
+                double dg = T[(o + lane) * LDT + o + lane];
 #pragma unroll
                 for (int j = 0; j < SB; ++j) {
-                    double d = __shfl_sync(0xffffffffu, a[j], j);
+                    double d = __shfl_sync(0xffffffffu, dg, j);
                     if (!(d > 0.0)) {   // not positive definite: remember the minor's order, keep going finite
                         if (lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + j + 1;
                         d = 1.0;
                     }
-                    const double rinv = rsqrt(d);
+                    const double rinv = pivot_rsqrt(d);
                     double l = 0.0;
                     if (lane > j) l = a[j] * rinv;
                     else if (lane == j) { l = d * rinv; rinvL[j] = rinv; }
+                    dg = fma(-l, l, dg);
                     if (lane >= j) T[(o + j) * LDT + o + lane] = l;
+                    if (j + 1 < SB) {
+                        const double ln = __shfl_sync(0xffffffffu, l, j + 1);
+                        a[j + 1] = fma(-l, ln, a[j + 1]);
+                    }
                     __syncwarp();
 #pragma unroll
-                    for (int c = j + 1; c < SB; ++c) a[c] = fma(-l, T[(o + j) * LDT + o + c], a[c]);
+                    for (int c = j + 2; c < SB; ++c) a[c] = fma(-l, T[(o + j) * LDT + o + c], a[c]);
                 }
             } else {
                 rinvL[lane] = 1.0 / T[(o + lane) * LDT + o + lane];
@@ -116,11 +137,9 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, i
         // ---- (c) rank-32 update of the columns to the right: T(r,c) -= sum_k XP(r,k) XP(c,k)
         //      for (r >= c) [block being factored] or (r < o+32) [E rows already started]
         const int c_first = o + SB;
-        const int ncg = (NB - c_first) / 4;   // column groups of 4
-        for (int q = tid; q < 32 * ncg; q += POTF2_THREADS) {
-            const int r0 = (q & 31) * 4;
-            const int c0 = c_first + (q >> 5) * 4;
-            if (r0 + 3 < c0 && r0 >= c_first) continue;   // wholly inside the not-yet-started E region
+        const int ncg = (NB - c_first) / 4;   // column groups of 4; one warp per group, lanes own rows lane + 32 i
+        for (int q = warp; q < ncg; q += POTF2_THREADS / 32) {
+            const int c0 = c_first + q * 4;
             double acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -128,21 +147,24 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, i
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 #pragma unroll 8
             for (int k = 0; k < SB; ++k) {
-                double xr[4], xc[4];
+                double xr[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xr[i] = XP[k * NB + r0 + i];
+                for (int i = 0; i < 4; ++i) xr[i] = XP[k * NB + lane + 32 * i];          // conflict-free
+                const double2 xc01 = *reinterpret_cast<const double2*>(&XP[k * NB + c0]);      // broadcast
+                const double2 xc23 = *reinterpret_cast<const double2*>(&XP[k * NB + c0 + 2]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xc[j] = XP[k * NB + c0 + j];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(xr[i], xc[j], acc[i][j]);
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fma(xr[i], xc01.x, acc[i][0]);
+                    acc[i][1] = fma(xr[i], xc01.y, acc[i][1]);
+                    acc[i][2] = fma(xr[i], xc23.x, acc[i][2]);
+                    acc[i][3] = fma(xr[i], xc23.y, acc[i][3]);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int r = r0 + i, c = c0 + j;
+                    const int r = lane + 32 * i, c = c0 + j;
                     if (r >= c || r < c_first) T[c * LDT + r] -= acc[i][j];
                 }
         }
@@ -150,6 +172,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, i
     }
 
     // ---- write back L (lower triangle of the valid part) and W = inv(L) (128x128, unit padded)
+#pragma unroll 8
     for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
         const int r = idx & (NB - 1), c = idx >> 7;
         if (FACTOR && r >= c && r < nb && c < nb) Mb[(long)(k0 + r) + (long)(k0 + c) * ld] = T[c * LDT + r];

@@ -126,8 +126,8 @@ int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const 
 /* ---- instrumentation ------------------------------------------------------------------------------- */
 /* timing of the last call on device 0 (CUDA events on the library's own streams), milliseconds / counts:
  *  [0] assembly kernel ms  [1] factorisation (all launches) ms  [2] trailing-update (DMMA) kernel ms summed
- *  [3] trailing-update launches  [4] trailing-update flops  [5] panel (POTF2+TRSM) ms  [6] total kernel launches
- *  [7] assembly launches.  Per-launch event timing is only taken when fgp_set_option("profile", 1). */
+ *  [3] trailing-update launches  [4] trailing-update flops  [5] diagonal-block (POTF2 + inverse) kernel ms summed
+ *  [6] panel-solve (TRSM as DMMA GEMM) ms summed  [7] kernel launches timed.  Per-launch event timing is only taken when fgp_set_option("profile", 1). */
 int fgp_get_timing(fgp_ctx* ctx, double* out8);
 /* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU). */
 int fgp_set_option(fgp_ctx* ctx, const char* name, double value);

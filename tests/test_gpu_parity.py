@@ -194,18 +194,23 @@ def test_premats_predict_simulate_loocv(ctx, spec):
 
 
 def test_not_positive_definite_reports_order(ctx):
-    """Duplicated training point + zero nugget: base::chol stops with 'leading minor of order k'; the batch keeps going."""
+    """A matrix that is not positive definite (duplicated training point, negative jitter): base::chol stops with
+    'the leading minor of order k is not positive definite'; the batched call flags the element and keeps going."""
     case = make_case(31, 200, 2, [], [], [], [])
     case["sIn"][150] = case["sIn"][20]
     Ms = oracle_dists(case)
     theta = theta_frac(Ms, 0.5)
     P = _problem(ctx, case)
     th = np.stack([theta, theta], axis=1)
-    nll, sig2, info = P.nll_batch("matern5_2", 0.0, th)
+    bad_nugget = -1e-6      # pushes the smallest eigenvalues clearly below zero: same failing minor in any summation order
+    nll, sig2, info = P.nll_batch("matern5_2", bad_nugget, th)
     with pytest.raises(ref.NotPosDef) as ei:
-        ref.negLogLik(theta, [], Ms, case["y"], "matern5_2", 0.0)
+        ref.negLogLik(theta, [], Ms, case["y"], "matern5_2", bad_nugget)
     assert info[0] == info[1] and info[0] > 0
-    assert abs(int(info[0]) - ei.value.order) <= 1 and np.isnan(nll[0])
+    assert int(info[0]) == ei.value.order and np.isnan(nll[0])
+    with pytest.raises(Exception) as e2:
+        P.premats("matern5_2", bad_nugget, 1.0, theta)
+    assert f"leading minor of order {ei.value.order}" in str(e2.value)
     # with the nugget the same data factorises
     nll2, _, info2 = P.nll_batch("matern5_2", 1e-8, theta)
     assert info2[0] == 0 and np.isfinite(nll2[0])

@@ -19,7 +19,8 @@ out["peaks"] = ctx.measure_peaks()
 print("peaks", out["peaks"], flush=True)
 
 
-def run(n, B, streams, lookahead, ker="gauss", reps=3, profile=False):
+def run(n, B, streams, lookahead, ker="gauss", reps=3, profile=False, outer=4):
+    ctx.set_option("outer", outer)
     ctx.set_option("streams", streams)
     ctx.set_option("lookahead", lookahead)
     ctx.set_option("profile", 1 if profile else 0)
@@ -35,7 +36,7 @@ def run(n, B, streams, lookahead, ker="gauss", reps=3, profile=False):
         ts.append(time.perf_counter() - t0)
     t = min(ts)
     fl = B * n ** 3 / 3.0
-    rec = dict(n=n, B=B, streams=streams, lookahead=lookahead, sec=t, evals_per_s=B / t, chol_tflops=fl / t / 1e12,
+    rec = dict(n=n, B=B, outer=outer, streams=streams, lookahead=lookahead, sec=t, evals_per_s=B / t, chol_tflops=fl / t / 1e12,
                info=int(info.max()), nll0=float(nll[0]))
     if profile:
         rec["timing"] = ctx.timing()
@@ -46,12 +47,13 @@ def run(n, B, streams, lookahead, ker="gauss", reps=3, profile=False):
 
 recs = []
 for n in (1024, 2048, 4096, 8192):
-    recs.append(run(n, 1, 1, 0))
-    recs.append(run(n, 1, 1, 1))
-    recs.append(run(n, 1, 1, 0, profile=True))
-for n, B in ((1024, 64), (2048, 20), (8192, 8), (8192, 13)):
-    for s in (1, 2, 4):
-        recs.append(run(n, B, s, 0))
+    for outer in (1, 2, 4):
+        recs.append(run(n, 1, 1, 1, outer=outer))
+    recs.append(run(n, 1, 1, 0, profile=True, outer=1))
+    recs.append(run(n, 1, 1, 0, profile=True, outer=4))
+for n, B in ((1024, 64), (2048, 20), (8192, 8)):
+    for outer in (1, 2, 4):
+        recs.append(run(n, B, 4, 0, outer=outer))
 out["runs"] = recs
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w"), indent=1, default=float)
