@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the funGp-b200 hot path (contract: see the task statement / DESIGN.md).
+
+Metric (BASELINE.json): negLogLik evaluations / second at n = 8192 on one GPU.
+Workload = BASELINE.json configs[2] sizes ("C3": n = 8192 training points, 4 scalar + 2 functional inputs of length
+100 projected on B-splines with p = 5, L2_bygroup, gauss kernel, nugget 1e-8, FP64).  One *step* = one
+finite-difference gradient of the likelihood as stats::optim evaluates it: 2d+1 = 13 length-scale vectors
+(theta, theta +- 1e-3 e_i), i.e. 13 independent evaluations of  assembly -> Cholesky -> L^-1 y -> log det  in one
+batched C-ABI call (fgp_nll_batch).  Every evaluation builds and factors its own 8192 x 8192 FP64 matrix (512 MiB,
+larger than the 126 MB L2, so nothing is served from cache between steps).
+
+  value   evaluations/s with the data set resident in HBM (fgp_problem created once); each step still copies the
+          13 x d length-scales in and 13 x (nll, sigma^2, info) out -- that is the call's interface.
+  e2e     the same through the reference-facing call sequence with HOST buffers only: every step creates the device
+          problem from host arrays (H2D of coordinates, Gram matrices and y), evaluates the batch, reads the results
+          back and destroys the problem.
+With --gpus N (torchrun, one process per GPU) every rank evaluates its own 13-point batch on its own GPU: independent
+work items, no collective on the data path; value = all ranks' evaluations / max-over-ranks time.
+
+--impl reference runs the CPU restatement of the reference (oracle/, numpy/scipy, all host threads) on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "negLogLik evals/sec at n=8192 (1 GPU)"
+UNIT = "evals/s"
+CFG = dict(n=8192, ds=4, f_lens=[100, 100], pdims=[5, 5], basis="B-splines", dis="L2_bygroup", ker="gauss", nugget=1e-8,
+           theta_frac=0.25, seed=8192)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=float(max(pw)))
+
+
+def build_inputs(rank=0):
+    """Host arrays of the C3 workload; projection through the library's own dimReduction (fgp_project)."""
+    from fungp_b200 import synth
+    sIn, fIn, y = synth.make_data(CFG["seed"], CFG["n"], CFG["ds"], CFG["f_lens"])
+    return sIn, fIn, y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fungp_b200
+    from fungp_b200 import synth
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    ctx = fungp_b200.Context(device_ids=[local_rank])
+    ctx.set_option("streams", args.streams)
+    ctx.set_option("outer", args.outer)
+    sIn, fIn, y = build_inputs()
+    n, ker, nug = CFG["n"], CFG["ker"], CFG["nugget"]
+    proj = [ctx.project(f, p, CFG["basis"]) for f, p in zip(fIn, CFG["pdims"])]
+    coefs = [c for (_, _, c) in proj]
+    J = [j for (_, j, _) in proj]
+    dis = [CFG["dis"]] * len(fIn)
+    P = fungp_b200.Problem(ctx, sIn, coefs, J, dis, y)
+    d = P.d
+    ub = 2.0 * P.dist_max()                       # setBounds_SF: upper = 2 max(D_l)
+    theta0 = CFG["theta_frac"] * ub * (1.0 + 0.003 * rank)
+    thetas = synth.fd_points(theta0, np.full(d, 1e-10), ub)        # d x (2d+1)
+    B = thetas.shape[1]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        nll, s2, info = P.nll_batch(ker, nug, thetas)
+        if info.any() or not np.all(np.isfinite(nll)):
+            raise SystemExit(f"bench.py: factorisation failed info={info}")
+        return nll
+
+    def step_e2e():
+        Pe = fungp_b200.Problem(ctx, sIn, coefs, J, dis, y)
+        nll, s2, info = Pe.nll_batch(ker, nug, thetas)
+        Pe.close()
+        return nll
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.mark(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nll_last = step_resident()
+    ctx.mark(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.elapsed_ms(0, 1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end arm (host buffers in, scalars out, every step)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+
+    # max over ranks
+    tt = torch.tensor([wall, dev_ms, wall_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall, dev_ms, wall_e2e = [float(x) for x in tt.cpu()]
+    total_evals = world * B * args.steps
+    # the step ends with a host-synchronous read of its results, so wall time >= device time; report the wall clock
+    value = total_evals / wall
+    e2e_value = total_evals / wall_e2e
+    h2d = 8 * (n * CFG["ds"] + sum(c.size for c in coefs) + sum(j.size for j in J) + n) + 8 * thetas.size
+    d2h = B * (8 + 8 + 4)
+
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel, measured live with CUDA events around every launch (separate pass)
+        peaks = ctx.measure_peaks()
+        ctx.set_option("profile", 1)
+        P.nll_batch(ker, nug, thetas[:, :2])
+        P.nll_batch(ker, nug, thetas[:, :2])
+        tm = ctx.timing()
+        ctx.set_option("profile", 0)
+        upd_tf = tm["update_flops"] / (tm["update_ms"] * 1e-3) / 1e12
+        asm_bytes = 2 * 8.0 * n * (n + 1) / 2          # two matrices in the profiled call
+        asm_gbs = asm_bytes / (tm["assembly_ms"] * 1e-3) / 1e9
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6650.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["update_kernel_dram_bytes_per_launch"]
+        except Exception:
+            pass
+        chol_flops = n ** 3 / 3.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2] sizes: fgpm likelihood at n=8192, 4 scalar + 2 functional "
+                                   "(len 100, B-splines p=5, L2_bygroup), gauss kernel, nugget 1e-8; one step = the 13 points of one "
+                                   "finite-difference gradient (2d+1, d=6) in one fgp_nll_batch call",
+                       "n": n, "d": int(d), "evals_per_step_per_gpu": int(B), "l2_policy": "inputs larger than L2: every evaluation "
+                       "writes and factors its own 512 MiB matrix", "streams": args.streams, "outer_panel_tiles": args.outer,
+                       "parallelism": f"theta-points sharded, {world} GPU(s), no collective"},
+            "device_ms_per_step": dev_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": wall_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (trailing update of the blocked Cholesky, FP64 DMMA m8n8k4)",
+                         "achieved": upd_tf, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s", "frac": upd_tf / peaks["dmma_tflops"],
+                         "traffic": traffic,
+                         "peak_source": "measured live: register-resident DMMA loop (fgp_measure_peaks); MEASURED_PEAKS.json has no FP64 "
+                                        "entry; nominal B200 FP64 = 37.2 TFLOP/s at 1965 MHz",
+                         "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
+                         "launch_ms_avg": tm["update_ms"] / max(1, tm["update_launches"]),
+                         "cholesky_tflops_whole_step": chol_flops * total_evals / wall / world / 1e12,
+                         "cholesky_frac_of_peak_whole_step": chol_flops * total_evals / wall / world / 1e12 / peaks["dmma_tflops"]},
+            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_kernel<gauss> (fused distance + correlation, lower triangle)",
+                                  "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
+                                  "algorithmic_bytes_per_launch": asm_bytes / 2, "launch_ms": tm["assembly_ms"] / 2,
+                                  "note": "FP64-issue co-bound: ~45 DFMA-class ops + one exp per 8-byte entry at d=6 (DESIGN.md)"},
+            "kernel_ms_profiled_2evals": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
+            "fp64_peaks_measured": peaks,
+            "nll_check": float(nll_last[0]),
+        }
+        if world == 1 and not args.skip_cpu:
+            out["cpu_baseline"] = cpu_baseline(sIn, coefs, J, y, thetas[:, 0], nll_last[0])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    P.close()
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_lists(sIn, coefs, J, rows=None):
+    from oracle import fungp_ref as ref
+    s1 = sIn if rows is None else sIn[:rows]
+    c1 = coefs if rows is None else [c[:rows] for c in coefs]
+    Ms = ref.setDistMatrix_S(s1, sIn) + ref.setDistMatrix_F(c1, coefs, J, [CFG["dis"]] * len(coefs))
+    return Ms
+
+
+def cpu_baseline(sIn, coefs, J, y, theta, nll_gpu):
+    """The oracle (literal numpy/scipy restatement of the reference's operation sequence) on the host cores: ONE
+    likelihood evaluation at n = 8192 with the materialised distance lists (built once, untimed, as fgpm() does)."""
+    from oracle import fungp_ref as ref
+    Ms = _oracle_lists(sIn, coefs, J)
+    t0 = time.perf_counter()
+    nll, s2 = ref.negLogLik(theta, [], Ms, y, CFG["ker"], CFG["nugget"])
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 full evaluation at n=8192 (setR over 6 materialised 8192^2 distance matrices, dpotrf, backsolve); numpy "
+                      "element-wise passes are single-threaded as in R, OpenBLAS uses all cores",
+            "seconds": dt, "nll": float(nll), "nll_rel_diff_vs_gpu": abs(nll - nll_gpu) / max(abs(nll), CFG["n"])}
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference (oracle/) on this box's host cores, rank 0 only.
+    Each step = a bounded sample of one evaluation: setR on the first f*n rows of every distance matrix (timed, scaled
+    by 1/f) + the full dpotrf / backsolve / log det on the assembled 8192^2 matrix (timed in full)."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import scipy.linalg as sla
+    from oracle import fungp_ref as ref
+    sIn, fIn, y = build_inputs()
+    bcj = ref.dimReduction(fIn, CFG["pdims"], [CFG["basis"]] * len(fIn))
+    J, coefs = bcj["J"], bcj["coefs"]
+    n = CFG["n"]
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    # full matrix once (untimed) for the factorisation part
+    Ms_full = _oracle_lists(sIn, coefs, J)
+    ub = np.array([2.0 * M.max() for M in Ms_full])
+    theta = CFG["theta_frac"] * ub
+    R = ref.corr_matrix(theta, Ms_full, CFG["ker"], CFG["nugget"])
+    del Ms_full
+
+    def chol_part():
+        t0 = time.perf_counter()
+        L = ref.r_chol_lower(R)
+        s2 = ref.analyticVar_llik(L, y, n)
+        ld = float(np.sum(np.log(np.diag(L))))
+        return time.perf_counter() - t0, 0.5 * (n * np.log(2 * np.pi * s2) + 2 * ld + n)
+    t_chol, nll = chol_part()
+    rows_probe = 256
+    Msp = _oracle_lists(sIn, coefs, J, rows_probe)
+    t0 = time.perf_counter(); ref.setR(theta, Msp, CFG["ker"]); t_probe = time.perf_counter() - t0
+    t_asm_full = t_probe * n / rows_probe
+    frac = min(1.0, max(0.03, (budget - t_chol) / t_asm_full))
+    rows = max(64, int(frac * n))
+    Ms = _oracle_lists(sIn, coefs, J, rows)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        Rs = ref.setR(theta, Ms, CFG["ker"])
+        Rs = Rs + 0.0   # the '+ diag(nugget)' pass of the reference touches the whole matrix once more
+        t_asm = (time.perf_counter() - t0) * n / rows
+        tc, nll = chol_part()
+        if it >= args.warmup:
+            times.append(t_asm + tc)
+    sec = float(np.mean(times))
+    out = {"impl": "reference", "metric": METRIC, "value": 1.0 / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[2] sizes: fgpm likelihood at n=8192, 4 scalar + 2 functional (len 100, "
+                                  "B-splines p=5, L2_bygroup), gauss kernel, nugget 1e-8; one step = one evaluation (CPU)", "n": n},
+           "cpu_baseline": {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"per step: setR on the first {rows} of {n} rows of each of the 6 distance matrices (scaled by "
+                                      f"{n / rows:.2f}) + full dpotrf/backsolve/logdet on the 8192^2 matrix; R is not installed on the "
+                                      "box, so this is the numpy/scipy restatement of the reference (oracle/)"},
+           "e2e": {"value": 1.0 / sec, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "nll_check": float(nll)}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--outer", type=int, default=4)
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,17 @@ class Context:
         return dict(assembly_ms=out[0], factor_ms=out[1], update_ms=out[2], update_launches=int(out[3]),
                     update_flops=out[4], potf2_ms=out[5], trsm_ms=out[6], launches=int(out[7]))
 
+    def launch_count(self):
+        return int(self.lib.fgp_launch_count())
+
+    def mark(self, idx):
+        self.check(self.lib.fgp_mark(self.h, idx), "fgp_mark")
+
+    def elapsed_ms(self, i, j):
+        ms = C.c_double()
+        self.check(self.lib.fgp_elapsed_ms(self.h, i, j, C.byref(ms)), "fgp_elapsed_ms")
+        return ms.value
+
     def measure_peaks(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self.check(self.lib.fgp_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)), "fgp_measure_peaks")

@@ -35,6 +35,8 @@ static inline long pick_ld(long rows) {
     return ld;
 }
 
+std::atomic<long long> g_fgp_launches{0};
+
 extern "C" const char* fgp_version(void) { return "fungp_b200 0.1 (sm_100a, FP64 DMMA)"; }
 
 // ------------------------------------------------------------------------------------------------ context
@@ -121,6 +123,34 @@ extern "C" int fgp_get_timing(fgp_ctx* ctx, double* out8) {
     out8[5] = ms[FgpTimers::PANEL];
     out8[6] = ms[FgpTimers::TRSM];
     out8[7] = cnt[FgpTimers::UPDATE] + cnt[FgpTimers::PANEL] + cnt[FgpTimers::TRSM] + cnt[FgpTimers::ASSEMBLY];
+    return 0;
+}
+
+extern "C" long long fgp_launch_count(void) { return g_fgp_launches.load(); }
+
+// device-side stopwatch over ALL of the library's streams on device 0: mark(i) records an event that follows every
+// stream's queued work; elapsed(i, j) is the CUDA-event time between two marks.
+extern "C" int fgp_mark(fgp_ctx* ctx, int idx) {
+    if (!ctx || idx < 0 || idx >= 4) return FGP_ERR_ARG;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    if (!d.evMark[idx]) CK(cudaEventCreate(&d.evMark[idx]));
+    for (int s = 0; s < DevState::MAXSTREAMS; ++s) {
+        CK(cudaEventRecord(d.evJoin[s], d.sPanel[s]));
+        CK(cudaStreamWaitEvent(d.sBulk, d.evJoin[s], 0));
+    }
+    CK(cudaEventRecord(d.evMark[idx], d.sBulk));
+    return 0;
+}
+extern "C" int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms) {
+    if (!ctx || !ms || i < 0 || j < 0 || i >= 4 || j >= 4) return FGP_ERR_ARG;
+    DevState& d = ctx->dev[0];
+    CK(cudaSetDevice(d.device));
+    if (!d.evMark[i] || !d.evMark[j]) return FGP_ERR_STATE;
+    CK(cudaEventSynchronize(d.evMark[j]));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, d.evMark[i], d.evMark[j]));
+    *ms = t;
     return 0;
 }
 

@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
 template <int MODE>
 void dispatch(const AsmK& k, int ker, dim3 grid, cudaStream_t st) {
     switch (ker) {
-        case 0: assemble_kernel<0, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
-        case 1: assemble_kernel<1, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
-        case 2: assemble_kernel<2, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
-        default: assemble_kernel<3, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
+        case 0: FGP_COUNT_LAUNCH(); assemble_kernel<0, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
+        case 1: FGP_COUNT_LAUNCH(); assemble_kernel<1, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
+        case 2: FGP_COUNT_LAUNCH(); assemble_kernel<2, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
+        default: FGP_COUNT_LAUNCH(); assemble_kernel<3, MODE><<<grid, ATHREADS, 0, st>>>(k); break;
     }
 }
 

@@ -300,29 +300,36 @@ __global__ void fill_identity_rows_kernel(double* M, long ld, long strideM, int 
 
 void launch_nll_reduce(const double* M, long ld, long strideM, int batch, int n, int yrow, const double* var_known,
                        const int* info, double* nll, double* sig2, cudaStream_t st) {
+    FGP_COUNT_LAUNCH();
     nll_reduce_kernel<<<batch, 256, 0, st>>>(M, ld, strideM, n, yrow, var_known, info, nll, sig2);
 }
 void launch_rownorm2(const double* M, long ld, int row0, int nrow, int ncol, int upper, double* out, cudaStream_t st) {
+    FGP_COUNT_LAUNCH();
     rownorm2_kernel<<<cdiv(nrow, 128), 128, 0, st>>>(M, ld, row0, nrow, ncol, upper, out);
 }
 void launch_rowgemv(const double* M, long ld, int row0, int nrow, int ncol, int upper, const double* z, long zstride,
                     double* out, cudaStream_t st) {
+    FGP_COUNT_LAUNCH();
     rowgemv_kernel<<<cdiv(nrow, 128), 128, 0, st>>>(M, ld, row0, nrow, ncol, upper, z, zstride, out);
 }
 void launch_lower_times(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean, double* sims,
                         cudaStream_t st) {
     dim3 grid(cdiv(m, 128), nsim);
+    FGP_COUNT_LAUNCH();
     lower_times_kernel<<<grid, 128, 0, st>>>(Lc, ld, m, Z, nsim, mean, sims);
 }
 void launch_extract_lower(const double* M, long ld, int n, double* out, cudaStream_t st) {
     const long tot = (long)n * n;
+    FGP_COUNT_LAUNCH();
     extract_lower_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, ld, n, out);
 }
 void launch_fill_yrow(double* M, long ld, long strideM, int batch, int row, const double* y, int n, cudaStream_t st) {
     dim3 grid(cdiv(n, 256), batch);
+    FGP_COUNT_LAUNCH();
     fill_yrow_kernel<<<grid, 256, 0, st>>>(M, ld, strideM, row, y, n);
 }
 void launch_fill_identity_rows(double* M, long ld, long strideM, int batch, int row0, int n, cudaStream_t st) {
     dim3 grid(cdiv(n, 128), n, batch);
+    FGP_COUNT_LAUNCH();
     fill_identity_rows_kernel<<<grid, 128, 0, st>>>(M, ld, strideM, row0, n);
 }

@@ -126,3 +126,8 @@ void launch_lower_times(const double* Lc, long ld, int m, const double* Z, int n
 void launch_extract_lower(const double* M, long ld, int n, double* out, cudaStream_t st);
 
 int fgp_peaks_device(double* dmma_tflops, double* dfma_tflops, double* copy_gbs);
+
+// number of kernels of this library launched by the process (bench.py reports it as gpu_launches)
+#include <atomic>
+extern std::atomic<long long> g_fgp_launches;
+#define FGP_COUNT_LAUNCH() (g_fgp_launches.fetch_add(1, std::memory_order_relaxed))

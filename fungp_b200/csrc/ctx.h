@@ -60,7 +60,7 @@ struct DevState {
     static const int MAXSTREAMS = 8;
     cudaStream_t sPanel[MAXSTREAMS] = {nullptr};
     cudaStream_t sBulk = nullptr;
-    cudaEvent_t evA = nullptr, evB = nullptr, evJoin[MAXSTREAMS] = {nullptr};
+    cudaEvent_t evA = nullptr, evB = nullptr, evJoin[MAXSTREAMS] = {nullptr}, evMark[4] = {nullptr};
     DevBuf work;      // factorisation workspaces (batch of trapezoids)
     DevBuf wbuf;      // inverse diagonal blocks
     DevBuf small;     // thetas / scales / results

@@ -280,5 +280,6 @@ void launch_gemm(const GemmArgs& g, cudaStream_t st) {
     const int ntiles = g.triT * (g.triT + 1) / 2 + (g.rectNR + g.rectNR1) * g.rectNC;
     if (ntiles <= 0 || g.batch <= 0) return;
     dim3 grid(ntiles, g.batch);
+    FGP_COUNT_LAUNCH();
     gemm_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
 }

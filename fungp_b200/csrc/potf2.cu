@@ -195,6 +195,7 @@ void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, d
         cudaFuncSetAttribute(potf2_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
         attr_set[dev] = true;
     }
+    FGP_COUNT_LAUNCH();
     potf2_inv_kernel<true><<<batch, POTF2_THREADS, POTF2_SMEM, st>>>(M, ld, strideM, k0, nb, 0, W, strideW, info, infoOff);
 }
 
@@ -207,6 +208,7 @@ void launch_trtri_tiles(const double* M, long ld, int ntiles, int ncolsValid, do
         cudaFuncSetAttribute(potf2_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
         attr_set[dev] = true;
     }
+    FGP_COUNT_LAUNCH();
     potf2_inv_kernel<false><<<ntiles, POTF2_THREADS, POTF2_SMEM, st>>>(const_cast<double*>(M), ld, 0, 0, 0, ncolsValid, W,
                                                                        0, nullptr, 0);
 }

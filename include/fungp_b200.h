@@ -129,7 +129,13 @@ int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const 
  *  [3] trailing-update launches  [4] trailing-update flops  [5] diagonal-block (POTF2 + inverse) kernel ms summed
  *  [6] panel-solve (TRSM as DMMA GEMM) ms summed  [7] kernel launches timed.  Per-launch event timing is only taken when fgp_set_option("profile", 1). */
 int fgp_get_timing(fgp_ctx* ctx, double* out8);
-/* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU). */
+/* kernels of this library launched by the process so far */
+long long fgp_launch_count(void);
+/* device-side stopwatch over all of the library's streams on device 0 (CUDA events): idx, i, j in 0..3 */
+int fgp_mark(fgp_ctx* ctx, int idx);
+int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
+/* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU),
+ * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128). */
 int fgp_set_option(fgp_ctx* ctx, const char* name, double value);
 /* measured FP64 peaks on device 0 for the roofline denominators: register-resident DMMA (m8n8k4) loop and
  * DFMA loop, TFLOP/s; and a device copy, GB/s. */

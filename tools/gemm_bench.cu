@@ -4,6 +4,7 @@
 #include <cstdlib>
 void fgp_set_err(fgp_ctx*, const std::string&) {}
 void fgp_set_err_cuda(fgp_ctx*, const char*, cudaError_t, const char*, int) {}
+std::atomic<long long> g_fgp_launches{0};
 int main(int argc, char** argv) {
     const int T = argc > 1 ? atoi(argv[1]) : 48;   // trailing tiles
     const int n = (T + 4) * 128;
