@@ -1,0 +1,121 @@
+"""CPU gate: the C-ABI library loads, exports every symbol include/fungp_b200.h declares, refuses to run without a
+GPU (no fallback), and its host-side pieces (B-spline design matrix, PCA basis, projection) match the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import fungp_ref as ref
+from helpers import docs_example_data, load_docs, load_models, MODEL_NAMES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from fungp_b200 import _lib
+    return _lib.load()
+
+
+def _declared_symbols():
+    h = open(os.path.join(ROOT, "include", "fungp_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(fgp_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_header_symbols_exported_and_bound(lib):
+    from fungp_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for nm in names:
+        assert hasattr(lib, nm), f"{nm} declared in include/fungp_b200.h but not exported"
+        assert nm in _lib.SIGNATURES, f"{nm} has no ctypes signature"
+    assert set(_lib.SIGNATURES) <= set(names)
+    assert b"sm_100a" in lib.fgp_version()
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import fungp_b200
+    with pytest.raises(fungp_b200.FgpError):
+        fungp_b200.Context(1)
+    h = C.c_void_p()
+    assert lib.fgp_ctx_create(1, None, C.byref(h)) == -3 and not h.value
+
+
+def _project(lib, f, p, bt, B=None):
+    from fungp_b200 import _lib
+    f = np.asfortranarray(f); n, k = f.shape; pp = p or k
+    Bo = np.zeros((k, pp), order="F"); J = np.zeros((pp, pp), order="F"); co = np.zeros((n, pp), order="F")
+    dp = lambda a: a.ctypes.data_as(_lib.c_dp)
+    rc = lib.fgp_project(None, dp(f), n, k, p, bt, None if B is None else dp(np.asfortranarray(B)), dp(Bo), dp(J), dp(co))
+    assert rc == 0
+    return Bo, J, co
+
+
+@pytest.mark.parametrize("k,p", [(10, 1), (10, 2), (10, 3), (22, 3), (22, 5), (100, 5), (200, 10), (50, 12)])
+def test_bspline_basis_matches_splineDesign(lib, k, p):
+    from fungp_b200 import _lib
+    B = np.zeros((k, p), order="F")
+    assert lib.fgp_bspline_basis(k, p, B.ctypes.data_as(_lib.c_dp)) == 0
+    np.testing.assert_allclose(B, ref.proj_bsplines(k, p), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(B.sum(axis=1), 1.0, atol=1e-13)     # partition of unity
+
+
+def test_docs_basis_and_coefs_through_c_abi(lib):
+    """docs/reference/fgpm.html: m1@f_proj@basis / @coefs printed to 7-8 digits."""
+    d = load_docs()
+    sIn, fIn, sOut, _ = docs_example_data()
+    for i in range(2):
+        Bo, J, co = _project(lib, fIn[i], 3, 1)
+        np.testing.assert_allclose(Bo, np.array(d["basis"][i]), rtol=0, atol=6e-8)
+        np.testing.assert_allclose(co, np.array(d["coefs"][i]), rtol=0, atol=6e-8)
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_stored_model_projection(lib, name):
+    g = load_models()[name]
+    if not g["df"]:
+        pytest.skip("scalar-only model")
+    for f, p, bt, Bg, cg in zip(g["fIn"], g["f_pdims"], g["f_basType"], g["basis"], g["coefs"]):
+        code = 2 if bt == "PCA" else 1
+        Bo, J, co = _project(lib, f, p, code)
+        sg = np.sign(np.sum(Bo * Bg, axis=0)) if code == 2 else 1.0      # quirk Q7: PCA sign is LAPACK's
+        np.testing.assert_allclose(Bo * sg, Bg, atol=1e-12)
+        np.testing.assert_allclose(co * sg, cg, atol=1e-11)
+        # re-projection with the stored basis (predict / simulate path)
+        _, _, co2 = _project(lib, f, p, code, B=Bg)
+        np.testing.assert_allclose(co2, cg, atol=1e-11)
+
+
+def test_pca_and_identity_projection(lib):
+    rng = np.random.default_rng(3)
+    f = rng.random((60, 18))
+    for p in (1, 3, 6):
+        Bo, J, co = _project(lib, f, p, 2)
+        r = ref.dimReduction([f], [p], ["PCA"])
+        sg = np.sign(np.sum(Bo * r["basis"][0], axis=0))
+        np.testing.assert_allclose(Bo * sg, r["basis"][0], atol=1e-12)
+        np.testing.assert_allclose(co * sg, r["coefs"][0], atol=1e-11)
+        np.testing.assert_allclose(J, np.eye(p), atol=1e-13)
+    Bo, J, co = _project(lib, f, 0, 1)
+    assert np.array_equal(co, f) and np.array_equal(Bo, np.eye(18)) and np.array_equal(J, np.eye(18))
+
+
+def test_fd_points_and_optimizer_wrapper_on_cpu_function():
+    """The batched L-BFGS-B driver (host logic) against the oracle's optimiser on an analytic function."""
+    from fungp_b200.model import optim_lbfgsb_batched, r_fd_points
+    lo, up = np.array([1e-10, 1e-10, 1e-10]), np.array([2.0, 3.0, 1.5])
+    f = lambda x: float((x[0] - 0.7) ** 2 + 3 * (x[1] - 2.9995) ** 2 + (x[2] - 5.0) ** 2 + 0.1 * x[0] * x[1])
+    pts = r_fd_points(np.array([0.5, 2.9999, 1.0]), lo, up)
+    assert pts.shape == (3, 7) and pts[1, 3] == 3.0 and abs(pts[1, 4] - 2.9989) < 1e-12
+    xb, fb, cb = optim_lbfgsb_batched(lambda P: np.array([f(P[:, j]) for j in range(P.shape[1])]), [1.0, 1.0, 1.0], lo, up)
+    xo, fo, co = ref.optim_lbfgsb(f, np.array([1.0, 1.0, 1.0]), lo, up)
+    np.testing.assert_allclose(xb, xo, rtol=1e-12)
+    assert fb == fo and cb == co and xb[2] == 1.5
