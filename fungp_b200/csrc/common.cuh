@@ -92,8 +92,6 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
 
 void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, double* W, long strideW, int* info,
                   int infoBase, cudaStream_t st);
-// W_k = inv(L_kk) for several already factored diagonal tiles at once (predict / simulate continuation)
-void launch_trtri_tiles(const double* M, long ld, int ntiles, int ncolsValid, double* W, cudaStream_t st);
 
 struct GemmArgs {
     const double* A; long lda; long strideA;   // row operand: element (r, kk) = A[r + kk*lda], r = global row

@@ -3,25 +3,35 @@
 // Replaces the unblocked part of base::chol / dpotrf (R/3_training_SF.R:249, R/4_prediction_SF.R:28,
 // R/5_simulation_SF.R:14) and of backsolve / dtrsm (R/3_training_SF.R:267, R/4_prediction_SF.R:9,29).
 //
-// One CTA per matrix.  The block lives in shared memory as a 128 x 129 column-major array T:
+// One CTA (8 warps) per matrix; this is the serial chain of the factorisation, so the design goal is latency:
+// shared-memory loads cost ~7 cycles of issue each on this part (measured, tools/lat_bench.cu), FP64 FMAs have 8
+// cycles of latency and a DMMA 26, hence: everything that is a matrix product goes through DMMA fragments, and the
+// only scalar code is the 32-column chain of step (a).
+//
+// The block lives in shared memory as a 128 x 132 column-major array T:
 //   lower triangle (r >= c): the block being factored -> L
-//   strict upper   (r <  c): E(r,c) = (L^-T)(r,c) = W(c,r); E starts as the identity (diagonal kept in dinvE)
-// Four sub-steps of 32 columns: (a) warp 0 factors the 32x32 diagonal sub-block, one lane per row, right-looking,
-// column broadcast through shared memory; (b) 128 threads, one per row, forward-substitute their 32 entries
-// (rows below the sub-block and the E rows); (c) all threads apply the rank-32 update to the columns to the right.
+//   strict upper   (r <  c): E(r,c) = (L^-T)(r,c) = W(c,r); E starts as the identity (its diagonal is kept in dinvE)
+// Four sub-steps s of 32 columns (o = 32 s):
+//   (a) warp 0, lane = row: right-looking Cholesky of the 32x32 diagonal sub-block AND, carried along with the same
+//       broadcast values, E_ss = L_ss^-T (so that (b) is a product).  Pivot chain in registers:
+//       dg -= l^2 -> shuffle -> rsqrt.approx + one cubic correction; the next column's last update via shuffle.
+//   (b) all warps, DMMA: X = B * E_ss for the 96 rows outside the sub-block (rows below: the L panel; rows above: E rows)
+//   (c) all warps, DMMA: rank-32 update T(r,c) -= X(r,:) X(c,:)' of the columns to the right, for (r >= c) [block being
+//       factored] or (r < o+32) [E rows that have started]
 #include "common.cuh"
 
 namespace {
 
 constexpr int NB = 128;
-constexpr int LDT = 129;
+constexpr int LDT = 132;     // == 4 (mod 16): DMMA A/B fragments read straight from T / XP without bank conflicts
 constexpr int SB = 32;
+constexpr int XLD = 132;     // XP[k][row]
+constexpr int ELD = 36;      // Eop[k][n]
 constexpr int POTF2_THREADS = 256;
-constexpr int POTF2_SMEM = (NB * LDT + NB * SB + SB + NB) * 8;
+constexpr int POTF2_SMEM = (NB * LDT + SB * XLD + SB * ELD + SB + NB) * 8;
 
 // 1/sqrt(d) for the pivots: MUFU seed (rsqrt.approx, ~2^-20 relative) + one cubically convergent correction, all
-// FMA.  This sits on the factorisation's only truly serial chain (one pivot per column), so its latency -- not its
-// throughput -- is what matters; the libdevice rsqrt() is ~2x longer.  Result within ~1 ulp.
+// FMA: 49 cycles of latency against 94 for the libdevice rsqrt() and 160 for sqrt() (tools/lat_bench.cu).
 __device__ __forceinline__ double pivot_rsqrt(double d) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
@@ -29,157 +39,223 @@ __device__ __forceinline__ double pivot_rsqrt(double d) {
     return fma(y * e, fma(0.375, e, 0.5), y);             // y (1 + e/2 + 3 e^2/8)
 }
 
-template <bool FACTOR>
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
-potf2_inv_kernel(double* M, long ld, long strideM, int k0_first, int nb_first, int ncolsValid, double* W,
-                 long strideW, int* info, int infoOff) {
+potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, long strideW, int* info, int infoOff) {
     extern __shared__ __align__(16) double sm[];
-    double* T = sm;                       // 128 x 129
-    double* XP = sm + NB * LDT;           // 128 x 32 staged panel (col-major, ld 128)
-    double* rinvL = XP + NB * SB;         // 32: 1/L_jj of the current sub-block
-    double* dinvE = rinvL + SB;           // 128: diagonal of L^-1
+    double* T = sm;                       // 128 x 132
+    double* XP = sm + NB * LDT;           // 32 x 132: XP[k*XLD + row] = staged panel X(row, k)
+    double* Eop = XP + SB * XLD;          // 32 x 36 : Eop[k*ELD + n] = E_ss(k, n)
+    double* dinvE = Eop + SB * ELD;       // 128: diagonal of L^-1
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int fr = lane >> 2;             // fragment row / n index
+    const int fk = lane & 3;              // fragment k index
+    double* Mb = M + (long)blockIdx.x * strideM;
+    double* Wb = W + (long)blockIdx.x * strideW + (long)(k0 / NB) * NB * NB;
 
-    // FACTOR: blockIdx.x = batch element, one tile (k0_first, nb_first)
-    // !FACTOR: blockIdx.x = tile index (all already factored), single matrix
-    int k0, nb;
-    double* Mb;
-    double* Wb;
-    if (FACTOR) {
-        k0 = k0_first;
-        nb = nb_first;
-        Mb = M + (long)blockIdx.x * strideM;
-        Wb = W + (long)blockIdx.x * strideW + (long)(k0 / NB) * NB * NB;
-    } else {
-        k0 = blockIdx.x * NB;
-        nb = min(NB, ncolsValid - k0);
-        Mb = M;
-        Wb = W + (long)blockIdx.x * NB * NB;
-    }
-
-    // ---- load: lower triangle of the block, identity padding, zeros above the diagonal
-#pragma unroll 16
-    for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
-        const int r = idx & (NB - 1), c = idx >> 7;
-        double v = 0.0;
-        if (r >= c) {
-            if (r < nb && c < nb) v = Mb[(long)(k0 + r) + (long)(k0 + c) * ld];
-            else if (r == c) v = 1.0;
+    // ---- load the lower triangle (identity padding for a ragged block, zeros above the diagonal)
+    if (nb == NB) {
+        // whole 16-byte row pairs, all in flight at once; the strict upper part is cleared afterwards
+        const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(T);
+        for (int idx = tid; idx < NB * NB / 2; idx += POTF2_THREADS) {
+            const int r = (idx & 63) * 2, c = idx >> 6;
+            if (r + 1 >= c) {
+                const double* src = Mb + (long)(k0 + r) + (long)(k0 + c) * ld;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(tbase + (uint32_t)((c * LDT + r) * 8)), "l"(src));
+            }
         }
-        T[c * LDT + r] = v;
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+            const int r = idx & (NB - 1), c = idx >> 7;
+            if (r < c) T[c * LDT + r] = 0.0;
+        }
+    } else {
+#pragma unroll 8
+        for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+            const int r = idx & (NB - 1), c = idx >> 7;
+            double v = 0.0;
+            if (r >= c) {
+                if (r < nb && c < nb) v = Mb[(long)(k0 + r) + (long)(k0 + c) * ld];
+                else if (r == c) v = 1.0;
+            }
+            T[c * LDT + r] = v;
+        }
     }
     __syncthreads();
 
     for (int s = 0; s < NB / SB; ++s) {
         const int o = s * SB;
-        // ---- (a) factor the 32x32 diagonal sub-block (warp 0), or just invert its diagonal
+        // ================= (a) 32x32 Cholesky + its inverse transpose, warp 0 =================
         if (warp == 0) {
-            if (FACTOR) {
-                // lane = row.  Two dependency chains per column, both kept in registers / shuffles:
-                //   pivots:  dg (this lane's own diagonal entry, updated with -l^2 every column) -> shfl -> rsqrt
-                //   column:  a[j+1] gets its last update from a shuffle of l, not from shared memory
-                // the remaining updates a[c], c > j+1, read column j back from shared memory (broadcast) off-chain.
-                double a[SB];
+            double a[SB], e[SB];
 #pragma unroll
-                for (int j = 0; j < SB; ++j) a[j] = T[(o + j) * LDT + o + lane];
-                double dg = T[(o + lane) * LDT + o + lane];
+            for (int j = 0; j < SB; ++j) {
+                a[j] = T[(o + j) * LDT + o + lane];
+                e[j] = (j == lane) ? 1.0 : 0.0;
+            }
+            double dg = T[(o + lane) * LDT + o + lane];
 #pragma unroll
-                for (int j = 0; j < SB; ++j) {
-                    double d = __shfl_sync(0xffffffffu, dg, j);
-                    if (!(d > 0.0)) {   // not positive definite: remember the minor's order, keep going finite
-                        if (lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + j + 1;
-                        d = 1.0;
-                    }
-                    const double rinv = pivot_rsqrt(d);
-                    double l = 0.0;
-                    if (lane > j) l = a[j] * rinv;
-                    else if (lane == j) { l = d * rinv; rinvL[j] = rinv; }
-                    dg = fma(-l, l, dg);
-                    if (lane >= j) T[(o + j) * LDT + o + lane] = l;
-                    if (j + 1 < SB) {
-                        const double ln = __shfl_sync(0xffffffffu, l, j + 1);
-                        a[j + 1] = fma(-l, ln, a[j + 1]);
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int c = j + 2; c < SB; ++c) a[c] = fma(-l, T[(o + j) * LDT + o + c], a[c]);
+            for (int j = 0; j < SB; ++j) {
+                double d = __shfl_sync(0xffffffffu, dg, j);
+                if (!(d > 0.0)) {   // not positive definite: remember the minor's order, keep going finite
+                    if (lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + j + 1;
+                    d = 1.0;
                 }
-            } else {
-                rinvL[lane] = 1.0 / T[(o + lane) * LDT + o + lane];
+                const double rinv = pivot_rsqrt(d);
+                double l = 0.0;
+                if (lane > j) l = a[j] * rinv;
+                else if (lane == j) l = d * rinv;
+                const double x = e[j] * rinv;          // E(lane, j); zero for lane > j
+                e[j] = x;
+                dg = fma(-l, l, dg);
+                if (lane >= j) T[(o + j) * LDT + o + lane] = l;
+                if (j + 1 < SB) {
+                    const double ln = __shfl_sync(0xffffffffu, l, j + 1);
+                    a[j + 1] = fma(-l, ln, a[j + 1]);
+                    e[j + 1] = fma(-x, ln, e[j + 1]);
+                }
+                __syncwarp();
+                // column j read back as 16-byte pairs (shared-memory loads are the scarce resource here)
+                if ((j + 2) & 1) {
+                    const double lc = T[(o + j) * LDT + o + j + 2];
+                    if (j + 2 < SB) { a[j + 2] = fma(-l, lc, a[j + 2]); e[j + 2] = fma(-x, lc, e[j + 2]); }
+                }
+#pragma unroll
+                for (int c = (j + 3) & ~1; c + 1 < SB; c += 2) {
+                    const double2 lc = *reinterpret_cast<const double2*>(&T[(o + j) * LDT + o + c]);
+                    a[c] = fma(-l, lc.x, a[c]);
+                    e[c] = fma(-x, lc.x, e[c]);
+                    a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                    e[c + 1] = fma(-x, lc.y, e[c + 1]);
+                }
+            }
+            // E_ss: strict upper part into T, diagonal into dinvE, operand copies for (b) and (c)
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                const double v = (j >= lane) ? e[j] : 0.0;
+                Eop[lane * ELD + j] = v;
+                XP[j * XLD + o + lane] = v;
+                if (j > lane) T[(o + j) * LDT + o + lane] = v;
+                if (j == lane) dinvE[o + lane] = v;
             }
         }
         __syncthreads();
-        // ---- (b) forward substitution, one thread per row: x L_ss' = b
-        if (tid < NB) {
-            const int r = tid;
-            const bool diagrow = (r >= o) && (r < o + SB);
-            double bvec[SB];
+        // ================= (b) X = B * E_ss for the rows outside the diagonal sub-block, DMMA =================
+        {
+            const int rbase = warp * 16;                         // this warp's 16 rows (two 8-row blocks)
+            const bool isdiag = (rbase >= o) && (rbase < o + SB);    // 16 | 32: uniform per warp
+            if (!isdiag) {
+                double af[2][8];
 #pragma unroll
-            for (int j = 0; j < SB; ++j) bvec[j] = diagrow ? ((r - o == j) ? 1.0 : 0.0) : T[(o + j) * LDT + r];
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int k = 0; k < SB; ++k) {
-                const double x = bvec[k] * rinvL[k];
-                bvec[k] = x;
+                    for (int k4 = 0; k4 < 8; ++k4) af[mi][k4] = T[(o + k4 * 4 + fk) * LDT + rbase + mi * 8 + fr];
+                double acc[2][4][2];
 #pragma unroll
-                for (int c = k + 1; c < SB; ++c) bvec[c] = fma(-x, T[(o + k) * LDT + o + c], bvec[c]);
-            }
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int k = 0; k < SB; ++k) {
-                XP[k * NB + r] = bvec[k];
-                if (!diagrow) T[(o + k) * LDT + r] = bvec[k];
-                else if (k > r - o) T[(o + k) * LDT + r] = bvec[k];
-                else if (k == r - o) dinvE[r] = bvec[k];
+                    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    double bf[4];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) bf[ni] = Eop[(k4 * 4 + fk) * ELD + ni * 8 + fr];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][k4], bf[ni]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = rbase + mi * 8 + fr, n = ni * 8 + 2 * fk + h;
+                            T[(o + n) * LDT + r] = acc[mi][ni][h];
+                            XP[n * XLD + r] = acc[mi][ni][h];
+                        }
             }
         }
         __syncthreads();
-        // ---- (c) rank-32 update of the columns to the right: T(r,c) -= sum_k XP(r,k) XP(c,k)
-        //      for (r >= c) [block being factored] or (r < o+32) [E rows already started]
+        // ================= (c) rank-32 update of the columns to the right, DMMA =================
         const int c_first = o + SB;
-        const int ncg = (NB - c_first) / 4;   // column groups of 4; one warp per group, lanes own rows lane + 32 i
-        for (int q = warp; q < ncg; q += POTF2_THREADS / 32) {
-            const int c0 = c_first + q * 4;
-            double acc[4][4];
+        const int nnb = (NB - c_first) / 8;                       // 8-column blocks to the right: 12, 8, 4, 0
+        if (nnb > 0) {
+            const int rbase = warp * 16;
+            double af[2][8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < SB; ++k) {
-                double xr[4];
+                for (int k4 = 0; k4 < 8; ++k4) af[mi][k4] = XP[(k4 * 4 + fk) * XLD + rbase + mi * 8 + fr];
+            for (int nb0 = 0; nb0 < nnb; nb0 += 4) {
+                // 16 rows x 32 columns at a time; skip when every entry is in the not-yet-started E region
+                const int cb = c_first + nb0 * 8;
+                if (rbase + 15 < cb && rbase >= c_first) continue;
+                double acc[2][4][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xr[i] = XP[k * NB + lane + 32 * i];          // conflict-free
-                const double2 xc01 = *reinterpret_cast<const double2*>(&XP[k * NB + c0]);      // broadcast
-                const double2 xc23 = *reinterpret_cast<const double2*>(&XP[k * NB + c0 + 2]);
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[i][0] = fma(xr[i], xc01.x, acc[i][0]);
-                    acc[i][1] = fma(xr[i], xc01.y, acc[i][1]);
-                    acc[i][2] = fma(xr[i], xc23.x, acc[i][2]);
-                    acc[i][3] = fma(xr[i], xc23.y, acc[i][3]);
+                    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    double bf[4];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) bf[ni] = XP[(k4 * 4 + fk) * XLD + cb + ni * 8 + fr];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][k4], bf[ni]);
                 }
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = rbase + mi * 8 + fr, c = cb + ni * 8 + 2 * fk + h;
+                            if (r >= c || r < c_first) T[c * LDT + r] -= acc[mi][ni][h];
+                        }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = lane + 32 * i, c = c0 + j;
-                    if (r >= c || r < c_first) T[c * LDT + r] -= acc[i][j];
-                }
         }
         __syncthreads();
     }
 
-    // ---- write back L (lower triangle of the valid part) and W = inv(L) (128x128, unit padded)
+    // ---- write back L (lower triangle of the valid part)
 #pragma unroll 8
     for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
         const int r = idx & (NB - 1), c = idx >> 7;
-        if (FACTOR && r >= c && r < nb && c < nb) Mb[(long)(k0 + r) + (long)(k0 + c) * ld] = T[c * LDT + r];
-        double w = 0.0;
-        if (r > c) w = T[r * LDT + c];          // W(r,c) = E(c,r), stored at T(row c, col r)
-        else if (r == c) w = dinvE[r];
-        Wb[idx] = w;
+        if (r >= c && r < nb && c < nb) Mb[(long)(k0 + r) + (long)(k0 + c) * ld] = T[c * LDT + r];
+    }
+    // ---- W = inv(L) (128x128 column-major, unit padded): W(r,c) = E(c,r) = T(row c, col r) for r > c.
+    //      Transposed through XP (33-stride staging) so that both the shared reads and the global writes are contiguous.
+    double* stage = XP;                                            // 128 x 33 doubles fit (4224 <= 32*132)
+    for (int q = 0; q < NB / SB; ++q) {
+        __syncthreads();
+        // stage[kk*33 + j] = T(row kk, col 32q + j)   (threads walk down kk: contiguous in T)
+        for (int idx = tid; idx < NB * SB; idx += POTF2_THREADS) {
+            const int kk = idx & (NB - 1), j = idx >> 7;
+            stage[kk * 33 + j] = T[(q * SB + j) * LDT + kk];
+        }
+        __syncthreads();
+        // W(r = 32q + j, c = kk): threads walk along j: contiguous in global
+        for (int idx = tid; idx < NB * SB; idx += POTF2_THREADS) {
+            const int j = idx & (SB - 1), kk = idx >> 5;
+            const int r = q * SB + j, c = kk;
+            double w = 0.0;
+            if (r > c) w = stage[kk * 33 + j];
+            else if (r == c) w = dinvE[r];
+            Wb[r + c * NB] = w;
+        }
     }
 }
 
@@ -191,24 +267,9 @@ void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, d
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < FGP_MAXDEV && !attr_set[dev]) {
-        cudaFuncSetAttribute(potf2_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
-        cudaFuncSetAttribute(potf2_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
+        cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
         attr_set[dev] = true;
     }
     FGP_COUNT_LAUNCH();
-    potf2_inv_kernel<true><<<batch, POTF2_THREADS, POTF2_SMEM, st>>>(M, ld, strideM, k0, nb, 0, W, strideW, info, infoOff);
-}
-
-void launch_trtri_tiles(const double* M, long ld, int ntiles, int ncolsValid, double* W, cudaStream_t st) {
-    static bool attr_set[FGP_MAXDEV] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < FGP_MAXDEV && !attr_set[dev]) {
-        cudaFuncSetAttribute(potf2_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
-        cudaFuncSetAttribute(potf2_inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
-        attr_set[dev] = true;
-    }
-    FGP_COUNT_LAUNCH();
-    potf2_inv_kernel<false><<<ntiles, POTF2_THREADS, POTF2_SMEM, st>>>(const_cast<double*>(M), ld, 0, 0, 0, ncolsValid, W,
-                                                                       0, nullptr, 0);
+    potf2_inv_kernel<<<batch, POTF2_THREADS, POTF2_SMEM, st>>>(M, ld, strideM, k0, nb, W, strideW, info, infoOff);
 }

@@ -35,8 +35,23 @@ def _rel(a, b, floor):
     return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), floor))
 
 
-def _nll_tol(nll_ref, n):
-    return 1e-9 * max(abs(nll_ref), n)
+def _nll_tol(nll_ref, n, floor=0.0):
+    """1e-9 relative to max(|nll|, n) (north star), widened to 20x the oracle's own rounding-noise floor when the
+    matrix is so ill-conditioned that LAPACK itself does not reproduce the value to 1e-9 under a row permutation
+    (SURVEY.md 8d 'tolerance hygiene')."""
+    return max(1e-9 * max(abs(nll_ref), n), 20.0 * floor)
+
+
+def _noise_floor(theta, Ms, y, ker, nug, trials=3):
+    """|nll(P R P') - nll(R)| of the ORACLE over a few random permutations: the legitimate rounding noise."""
+    base = ref.negLogLik(theta, [], Ms, y, ker, nug)[0]
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for _ in range(trials):
+        p = rng.permutation(y.size)
+        v = ref.negLogLik(theta, [], [M[np.ix_(p, p)] for M in Ms], y[p], ker, nug)[0]
+        worst = max(worst, abs(v - base))
+    return worst
 
 
 def _log(test, **kw):
@@ -126,9 +141,11 @@ def test_assemble_and_nll(ctx, spec):
     assert nll[0] == nll[2] and sig2[0] == sig2[2]
     for b in (0, 1):
         r_nll, r_s2 = ref.negLogLik(th[:, b], [], Ms, case["y"], ker, nug)
-        assert abs(nll[b] - r_nll) <= _nll_tol(r_nll, n), (nll[b], r_nll)
-        assert abs(sig2[b] - r_s2) <= 1e-8 * r_s2
-        _log("assemble_and_nll", n=n, ker=ker, nll=r_nll, nll_abs_err=abs(nll[b] - r_nll), sig2_rel=abs(sig2[b] - r_s2) / r_s2)
+        floor = _noise_floor(th[:, b], Ms, case["y"], ker, nug) if n <= 1100 else 0.0
+        assert abs(nll[b] - r_nll) <= _nll_tol(r_nll, n, floor), (nll[b], r_nll, floor)
+        assert abs(sig2[b] - r_s2) <= max(1e-8, 40.0 * floor / n) * r_s2
+        _log("assemble_and_nll", n=n, ker=ker, nll=r_nll, nll_abs_err=abs(nll[b] - r_nll), sig2_rel=abs(sig2[b] - r_s2) / r_s2,
+             oracle_noise_floor=floor)
     # single-point call (look-ahead path) agrees with the batched call to rounding
     nll1, s21, _ = P.nll_batch(ker, nug, theta)
     assert abs(nll1[0] - nll[0]) <= 1e-11 * max(abs(nll[0]), n)
