@@ -105,6 +105,37 @@ class Context:
         self.check(self.lib.fgp_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)), "fgp_measure_peaks")
         return dict(dmma_tflops=a.value, dfma_tflops=b.value, copy_gbs=c.value)
 
+    def fit_batch(self, sIn, fIn, y, ants, u01, nugget=1e-8, n_starts=1, n_presample=20, dmax=None):
+        """fgp_fit_batch: score candidate structures (rows of `ants`, wire format of formatSol_ACO).
+        u01: list with one array per candidate (d_c * max(n_presample, n_starts) uniform draws, column-major d_c x n).
+        -> dict(fitness, nll, sig2, theta (n_cand x dmax), info)"""
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
+        n = y.size
+        s = None if sIn is None else _f(np.asarray(sIn, dtype=np.float64).reshape(n, -1))
+        ds = 0 if s is None else s.shape[1]
+        fs = [_f(f) for f in (fIn or [])]
+        df = len(fs)
+        ants = np.ascontiguousarray(np.asarray(ants, dtype=np.int32).reshape(-1, ds + 4 * df + 1))
+        nc = ants.shape[0]
+        off = np.zeros(nc, dtype=np.int64)
+        flat = []
+        pos = 0
+        for c in range(nc):
+            off[c] = pos
+            uc = np.asarray(u01[c], dtype=np.float64).ravel()
+            flat.append(uc); pos += uc.size
+        flat = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1)
+        if dmax is None:
+            dmax = ds + sum(f.shape[1] for f in fs)
+        k = (C.c_int * max(1, df))(*[f.shape[1] for f in fs])
+        fit = np.zeros(nc); nll = np.zeros(nc); s2 = np.zeros(nc); th = np.zeros((nc, dmax)); info = np.zeros(nc, dtype=np.int32)
+        rc = self.lib.fgp_fit_batch(self.h, n, ds, None if s is None else _dp(s), df, k, _dpp(fs), _dp(y), nc,
+                                    ants.ctypes.data_as(_lib.c_ip), float(nugget), int(n_starts), int(n_presample), _dp(flat),
+                                    off.ctypes.data_as(C.POINTER(C.c_longlong)), int(dmax), _dp(fit), _dp(nll), _dp(s2), _dp(th),
+                                    info.ctypes.data_as(_lib.c_ip))
+        self.check(rc, "fgp_fit_batch")
+        return dict(fitness=fit, nll=nll, sig2=s2, theta=th, info=info)
+
     # ---- dimension reduction (R/7_dimRedFunctions.R)
     def bspline_basis(self, k, p):
         B = np.zeros((k, p), order="F")

@@ -103,6 +103,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     if (!ctx || !name) return FGP_ERR_ARG;
     if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
+    else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "streams")) ctx->streams = std::max(1, std::min((int)value, (int)DevState::MAXSTREAMS));
     else { fgp_set_err(ctx, std::string("unknown option ") + name); return FGP_ERR_ARG; }
@@ -741,11 +742,4 @@ extern "C" int fgp_loocv(fgp_problem* P, double* y_pre, double* q2) {
     }
     if (q2) *q2 = 1.0 - (se / n) / (st2 / n);
     return 0;
-}
-
-extern "C" int fgp_fit_batch(fgp_ctx* ctx, int, int, const double*, int, const int*, const double* const*,
-                             const double*, int, const int*, double, int, int, const double*, const long long*, int,
-                             double*, double*, double*, double*, int*) {
-    fgp_set_err(ctx, "fgp_fit_batch: not built yet");
-    return FGP_ERR_STATE;
 }

@@ -77,6 +77,7 @@ struct fgp_ctx {
     int profile = 0;
     int lookahead = 1;
     int streams = 4;
+    int fit_workers = 4;      // fgp_fit_batch: concurrent candidate fits per GPU
     int outer = 4;            // column tiles per outer panel (trailing update K = outer*128)
     double timing[8] = {0};
     std::mutex mu;

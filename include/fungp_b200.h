@@ -112,12 +112,16 @@ int fgp_loocv(fgp_problem* prob, double* y_pre, double* q2);
  * format of formatSol_ACO (R/3_ant_admin.R:301-373): ints of length ds + 4*df + 1 --
  *   State X_i (1 on, 2 off) | per functional input: State, Dist (1 bygroup, 2 byindex), Dim, Basis (1 B-splines,
  *   2 PCA), -1 when off | Kernel (1 gauss, 2 matern5_2, 3 matern3_2).
- * For every candidate: projection -> presample (u01 = the runif(d*n_presample) draws made by R in ant order, so
- * the R RNG stream is unchanged; column-major d x n_presample per candidate, concatenated; offsets in u01_off) ->
+ * ants is n_cand x (ds + 4*df + 1), one candidate per row (row-major).  fIn[j] is the raw n x k[j] curve matrix.
+ * For every candidate: projection -> presample (u01 = the runif(d * max(n_presample, n_starts)) draws made by R in ant
+ * order, so the R RNG stream is unchanged; column-major d x n_presample per candidate, concatenated; u01_off[c] = offset
+ * of candidate c in doubles; d = its number of length-scales) ->
  * L-BFGS-B fit from the best n_starts points (lmm 5, factr 1e7, pgtol 0, maxit 100, central finite differences
  * with ndeps 1e-3 clipped at the box, as stats::optim does) -> preMats -> Q2loocv.
- * Outputs per candidate: fitness (Q2, NaN on crash), nll, sig2, theta (padded to dmax), info. Candidates are
- * dealt to the context's GPUs from a host-side queue. */
+ * Outputs per candidate: fitness (Q2, NaN on crash), nll, sig2, theta (dmax per candidate, NaN padded), info (0, the
+ * failing minor's order, or < 0: -1 bad structure, -4 more than dmax length-scales, -5 every start crashed).
+ * Candidates are dealt from a host-side queue to `fit_workers` (option, default 4) worker threads per GPU of the
+ * context, each with its own streams and workspaces; GPUs exchange nothing. */
 int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
                   const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
                   const double* u01, const long long* u01_off, int dmax, double* fitness, double* nll, double* sig2,
@@ -135,7 +139,7 @@ long long fgp_launch_count(void);
 int fgp_mark(fgp_ctx* ctx, int idx);
 int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
 /* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU),
- * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128). */
+ * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128), "fit_workers" (1..16). */
 int fgp_set_option(fgp_ctx* ctx, const char* name, double value);
 /* measured FP64 peaks on device 0 for the roofline denominators: register-resident DMMA (m8n8k4) loop and
  * DFMA loop, TFLOP/s; and a device copy, GB/s. */
