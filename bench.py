@@ -16,6 +16,7 @@ larger than the 126 MB L2, so nothing is served from cache between steps).
           back and destroys the problem.
 With --gpus N (torchrun, one process per GPU) every rank evaluates its own 13-point batch on its own GPU: independent
 work items, no collective on the data path; value = all ranks' evaluations / max-over-ranks time.
+torch.distributed is used for the barrier and the max over ranks only.
 
 --impl reference runs the CPU restatement of the reference (oracle/, numpy/scipy, all host threads) on rank 0.
 """
@@ -89,6 +90,46 @@ class ClockSampler:
                     power_w_max=float(max(pw)))
 
 
+FACTORY = dict(n=1024, ds=5, f_lens=[10, 22, 50], seed=1024, n_starts=1, n_presample=20, nugget=1e-8)
+
+
+def factory_candidates(n_cand, seed=7):
+    """Fixed pre-generated list of candidate structures for BASELINE.json configs[3] (5 scalar + 3 functional inputs):
+    random draws over the reference's solution space (state, distance, projection dimension, basis, kernel)."""
+    from fungp_b200 import factory as F
+    rng = np.random.default_rng(seed)
+    ds, df, lens = FACTORY["ds"], len(FACTORY["f_lens"]), FACTORY["f_lens"]
+    ants = []
+    while len(ants) < n_cand:
+        s_act = [i for i in range(ds) if rng.random() < 0.6]
+        f_act = [j for j in range(df) if rng.random() < 0.6]
+        if not s_act and not f_act:
+            continue
+        dis = [["L2_bygroup", "L2_byindex"][rng.integers(2)] for _ in f_act]
+        pd = [int(rng.integers(1, min(6, lens[j]) + 1)) for j in f_act]
+        bas = [["B-splines", "PCA"][rng.integers(2)] for _ in f_act]
+        ker = ["gauss", "matern5_2", "matern3_2"][rng.integers(3)]
+        ants.append(F.encode_ant(ds, df, s_act, f_act, dis, pd, bas, ker))
+    return np.stack(ants)
+
+
+def run_factory(ctx, rank, world, cands_per_gpu, barrier):
+    """fgpm_factory candidate scoring (second headline metric): n = 1024, candidates sharded over the ranks."""
+    from fungp_b200 import synth, factory as F
+    from fungp_b200.shard import shard_range
+    from fungp_b200.model import NumpyRng
+    sIn, fIn, y = synth.make_data(FACTORY["seed"], FACTORY["n"], FACTORY["ds"], FACTORY["f_lens"])
+    ants = factory_candidates(cands_per_gpu * world)
+    b0, b1 = shard_range(len(ants), rank, world)
+    F.score_candidates(ctx, sIn, fIn, y, ants[b0:b0 + 2], NumpyRng(0), nugget=FACTORY["nugget"])       # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    res = F.score_candidates(ctx, sIn, fIn, y, ants[b0:b1], NumpyRng(rank + 1), nugget=FACTORY["nugget"],
+                             n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"])
+    barrier()
+    return time.perf_counter() - t0, len(ants), int((res["info"] == 0).sum()), float(np.nanmax(res["fitness"]))
+
+
 def build_inputs(rank=0):
     """Host arrays of the C3 workload; projection through the library's own dimReduction (fgp_project)."""
     from fungp_b200 import synth
@@ -107,7 +148,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        # the data path has no collective (independent work items per GPU): the process group only carries the barrier
+        # and the max-over-ranks of three timing scalars, so gloo on host tensors is enough (and prints no banner)
+        dist.init_process_group(backend="gloo")
     ctx = fungp_b200.Context(device_ids=[local_rank])
     ctx.set_option("streams", args.streams)
     ctx.set_option("outer", args.outer)
@@ -170,11 +213,21 @@ def run_ours(args):
     barrier()
     wall_e2e = time.perf_counter() - t1
 
+    fac = None
+    if args.factory_cands > 0:
+        fac = run_factory(ctx, rank, world, args.factory_cands, barrier)
     # max over ranks
-    tt = torch.tensor([wall, dev_ms, wall_e2e], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([wall, dev_ms, wall_e2e], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     wall, dev_ms, wall_e2e = [float(x) for x in tt.cpu()]
+    if fac is not None:
+        ft = torch.tensor([fac[0]], dtype=torch.float64)
+        fo = torch.tensor([float(fac[2])], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fo, op=dist.ReduceOp.SUM)
+        fac = (float(ft.item()), fac[1], int(fo.item()), fac[3])
     total_evals = world * B * args.steps
     # the step ends with a host-synchronous read of its results, so wall time >= device time; report the wall clock
     value = total_evals / wall
@@ -237,6 +290,12 @@ def run_ours(args):
             "fp64_peaks_measured": peaks,
             "nll_check": float(nll_last[0]),
         }
+        if fac is not None:
+            out["factory"] = {"metric": "fgpm_factory candidates/sec", "value": fac[1] / fac[0], "unit": "candidates/s",
+                              "candidates": fac[1], "fitted_ok": fac[2], "seconds": fac[0], "n_gpus": world,
+                              "config": "BASELINE.json configs[3] sizes: n=1024, 5 scalar + 3 functional (len 10/22/50) candidate "
+                                        "structures from a fixed pre-generated list, full fit (presample 20, L-BFGS-B, preMats) + "
+                                        "Q2loocv per candidate via fgp_fit_batch; candidates sharded over ranks, no collective"}
         if world == 1 and not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(sIn, coefs, J, y, thetas[:, 0], nll_last[0])
     if world > 1:
@@ -337,8 +396,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4)
-    ap.add_argument("--outer", type=int, default=4)
+    ap.add_argument("--outer", type=int, default=8)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--factory-cands", type=int, default=48, help="candidate structures per GPU for the factory metric (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

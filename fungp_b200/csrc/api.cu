@@ -90,7 +90,7 @@ extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
         if (d.sBulk) cudaStreamDestroy(d.sBulk);
         if (d.evA) cudaEventDestroy(d.evA);
         if (d.evB) cudaEventDestroy(d.evB);
-        d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release();
+        d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release(); d.pool.release();
         if (d.pinned) cudaFreeHost(d.pinned);
     }
     delete ctx;
@@ -105,6 +105,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
+    else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "streams")) ctx->streams = std::max(1, std::min((int)value, (int)DevState::MAXSTREAMS));
     else { fgp_set_err(ctx, std::string("unknown option ") + name); return FGP_ERR_ARG; }
     return 0;
@@ -198,12 +199,17 @@ int problem_upload(fgp_problem* P, int slot) {
     ProblemDev& pd = P->pd[slot];
     if (pd.ready) return 0;
     CK(cudaSetDevice(ctx->dev[slot].device));
-    CK(cudaMalloc(&pd.X, sizeof(double) * std::max<size_t>(1, P->X.size())));
-    CK(cudaMalloc(&pd.units, sizeof(FgpUnit) * std::max<size_t>(1, P->units.size())));
-    CK(cudaMalloc(&pd.y, sizeof(double) * P->n));
-    CK(cudaMemcpy(pd.X, P->X.data(), sizeof(double) * P->X.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd.units, P->units.data(), sizeof(FgpUnit) * P->units.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(pd.y, P->y.data(), sizeof(double) * P->n, cudaMemcpyHostToDevice));
+    DevPool& pool = ctx->dev[slot].pool;
+    pd.X = (double*)pool.get(sizeof(double) * std::max<size_t>(1, P->X.size()));
+    pd.units = (FgpUnit*)pool.get(sizeof(FgpUnit) * std::max<size_t>(1, P->units.size()));
+    pd.y = (double*)pool.get(sizeof(double) * P->n);
+    if (!pd.X || !pd.units || !pd.y) { fgp_set_err(ctx, "out of device memory"); return FGP_ERR_ALLOC; }
+    // stream-ordered + synchronised: the consumers run on non-blocking streams that do not wait for the default stream
+    cudaStream_t up = ctx->dev[slot].sPanel[0];
+    CK(cudaMemcpyAsync(pd.X, P->X.data(), sizeof(double) * P->X.size(), cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(pd.units, P->units.data(), sizeof(FgpUnit) * P->units.size(), cudaMemcpyHostToDevice, up));
+    CK(cudaMemcpyAsync(pd.y, P->y.data(), sizeof(double) * P->n, cudaMemcpyHostToDevice, up));
+    CK(cudaStreamSynchronize(up));
     pd.ready = true;
     return 0;
 }
@@ -256,13 +262,14 @@ extern "C" void fgp_problem_destroy(fgp_problem* P) {
     for (size_t s = 0; s < P->pd.size(); ++s) {
         ProblemDev& pd = P->pd[s];
         if (!pd.ready && !pd.Lfac) continue;
-        cudaSetDevice(P->ctx->dev[s].device);
-        cudaDeviceSynchronize();
-        if (pd.X) cudaFree(pd.X);
-        if (pd.units) cudaFree(pd.units);
-        if (pd.y) cudaFree(pd.y);
-        if (pd.Lfac) cudaFree(pd.Lfac);
-        if (pd.Wall) cudaFree(pd.Wall);
+        DevState& d = P->ctx->dev[s];
+        cudaSetDevice(d.device);
+        // every call on this problem has synchronised its streams before returning: the blocks go back to the pool
+        if (pd.X) d.pool.put(pd.X);
+        if (pd.units) d.pool.put(pd.units);
+        if (pd.y) d.pool.put(pd.y);
+        if (pd.Lfac) d.pool.put(pd.Lfac);
+        if (pd.Wall) d.pool.put(pd.Wall);
     }
     delete P;
 }
@@ -277,7 +284,8 @@ extern "C" int fgp_problem_set_y(fgp_problem* P, const double* y) {
     for (size_t s = 0; s < P->pd.size(); ++s)
         if (P->pd[s].ready) {
             CK(cudaSetDevice(ctx->dev[s].device));
-            CK(cudaMemcpy(P->pd[s].y, y, sizeof(double) * P->n, cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(P->pd[s].y, y, sizeof(double) * P->n, cudaMemcpyHostToDevice, ctx->dev[s].sPanel[0]));
+            CK(cudaStreamSynchronize(ctx->dev[s].sPanel[0]));
         }
     P->hasModel = false;
     return 0;
@@ -397,13 +405,15 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
     std::vector<double> hScale((size_t)chunk * nt);
     const bool prof = ctx->profile != 0;
     if (prof) d.timers.reset();
-    if (var_known) CK(cudaMemcpy(dVar, var_known, sizeof(double), cudaMemcpyHostToDevice));
+    const double hVar = var_known ? *var_known : 0.0;
 
     for (int c0 = 0; c0 < B; c0 += chunk) {
         const int cb = std::min(chunk, B - c0);
         for (int i = 0; i < cb; ++i) kernel_scales(ker, nt, thetas + (size_t)(b0 + c0 + i) * nt, &hScale[(size_t)i * nt]);
-        CK(cudaMemcpy(dScale, hScale.data(), sizeof(double) * (size_t)cb * nt, cudaMemcpyHostToDevice));
-        CK(cudaMemset(dInfo, 0, sizeof(int) * cb));
+        // NOTE: every host->device copy below is issued on the stream that consumes it.  The library's streams are
+        // non-blocking: they do not wait for the legacy default stream, and a cudaMemcpy from pageable memory may return
+        // before its DMA has landed -- kernels on another stream would then read the previous batch's length-scales
+        // (seen under concurrent fgp_fit_batch workers).
         // split the chunk over streams so that one group's panel phase overlaps another group's trailing update
         int ns = prof ? 1 : std::min(ctx->streams, cb);
         if ((long)n * n < 512L * 512L) ns = 1;   // tiny matrices: one batched launch sequence is enough
@@ -414,6 +424,10 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             const int gb = g1 - g0;
             cudaStream_t st = d.sPanel[s];
             double* Mg = (double*)d.work.p + (size_t)g0 * ld * n;
+            CK(cudaMemcpyAsync(dScale + (size_t)g0 * nt, hScale.data() + (size_t)g0 * nt, sizeof(double) * (size_t)gb * nt,
+                               cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(dInfo + g0, 0, sizeof(int) * gb, st));
+            if (var_known) CK(cudaMemcpyAsync(dVar, &hVar, sizeof(double), cudaMemcpyHostToDevice, st));
             AsmArgs a = train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
             a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
             if (prof) d.timers.begin(st);
@@ -476,8 +490,9 @@ extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, 
     const long ld = pick_ld(n + 1);
     const int ncT = cdiv(n, FGP_TILE);
     if (!pd.Lfac) {
-        CK(cudaMalloc(&pd.Lfac, sizeof(double) * (size_t)ld * n));
-        CK(cudaMalloc(&pd.Wall, sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE));
+        pd.Lfac = (double*)d.pool.get(sizeof(double) * (size_t)ld * n);
+        pd.Wall = (double*)d.pool.get(sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE);
+        if (!pd.Lfac || !pd.Wall) { fgp_set_err(ctx, "fgp_premats: out of device memory"); return FGP_ERR_ALLOC; }
         pd.ldL = ld;
     }
     if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
@@ -526,7 +541,8 @@ static int upload_new(fgp_problem* P, DevState& d, int m, const double* sNew, co
     std::vector<double> X;
     build_coords(P, m, sNew, coefsNew, X);
     if (d.aux.ensure(sizeof(double) * std::max<size_t>(1, X.size()))) return FGP_ERR_ALLOC;
-    CK(cudaMemcpy(d.aux.p, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(d.aux.p, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice, d.sPanel[0]));
+    CK(cudaStreamSynchronize(d.sPanel[0]));
     *Xnew_dev = (double*)d.aux.p;
     return 0;
 }

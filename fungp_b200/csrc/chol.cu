@@ -11,6 +11,7 @@
 // the trailing update leaves the Schur complement there, which the same loop then factors.
 #include "common.cuh"
 #include "ctx.h"
+#include <functional>
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -31,7 +32,8 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     const bool colHole = t.colHoleHi > t.colHoleLo || (t.colHoleLo < t.ncols);
     const int colSegTile = (t.colHoleLo < t.ncols) ? t.colHoleHi / NBk : ncT;   // first tile of the second column segment
     FgpTimers* tm = ctx->profile ? &ctx->dev[devslot].timers : nullptr;
-    const int outer = std::max(1, ctx->outer);
+    const bool la_pre = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;
+    const int outer = std::max(1, la_pre ? ctx->outer_single : ctx->outer);
     (void)colHole;
 
     auto col_nb = [&](int k) {
@@ -118,11 +120,28 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
         if (k < t.cpre) kend = std::min(kend, t.cpre);
         if (k < colSegTile) kend = std::min(kend, colSegTile);
         int Kpanel = 0;
-        for (int kk = k; kk < kend; ++kk) {
+        for (int kk = k; kk < kend; ++kk) Kpanel += std::max(0, col_nb(kk));
+        // recursive panel: a range of more than one tile is split in halves; the right half is updated with the whole
+        // left half at once (K = 128 * tiles), so narrow-K updates only ever touch narrow column ranges
+        std::function<void(int, int)> factor_range = [&](int a, int b) {
+            if (b - a > 1) {
+                const int mid = a + (b - a + 1) / 2;
+                factor_range(a, mid);
+                int Kl = 0;
+                for (int kk = a; kk < mid; ++kk) Kl += std::max(0, col_nb(kk));
+                if (Kl > 0) {
+                    GemmArgs g = make_update(a, Kl, rows_of(mid - 1), mid, b);
+                    if (tm) tm->begin(sPanel);
+                    launch_gemm(g, sPanel);
+                    if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
+                }
+                factor_range(mid, b);
+                return;
+            }
+            const int kk = a;
             const int k0 = kk * NBk;
             const int nb = col_nb(kk);
-            if (nb <= 0) continue;
-            Kpanel += nb;
+            if (nb <= 0) return;
             const bool fresh = kk >= t.cpre;
             // -- diagonal block
             if (fresh) {
@@ -133,35 +152,27 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
             }
             const RowSet S = rows_of(kk);
             // -- panel solve X = P * W_k'  (tile kk itself takes part when its block is ragged: rows below k0+nb)
-            {
-                GemmArgs g = base;
-                g.A = t.M + (long)k0 * t.ld;
-                g.B = t.W + (long)kk * NBk * NBk; g.ldb = NBk; g.strideB = t.strideW;
-                g.C = t.M + (long)k0 * t.ld;
-                g.K = nb; g.accumulate = 0;
-                g.tri0 = 0; g.triT = 0;
-                int tlo1 = S.lo1, thi1 = S.hi1;
-                if (fresh && nb < NBk && (long)k0 + nb < (long)std::min(t.nrows, (kk + 1) * NBk)) {
-                    if (thi1 > tlo1) tlo1 = kk; else { tlo1 = kk; thi1 = kk + 1; }
-                }
-                g.rectR0 = tlo1; g.rectNR = thi1 - tlo1; g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2;
-                g.rectC0 = kk; g.rectNC = 1; g.bTileBase = kk;
-                g.rowMin = k0 + nb;
-                g.colMin = 0; g.colLo = nb; g.colHoleHi = nb; g.ncols = nb;
-                if (g.rectNR + g.rectNR1 > 0) {
-                    if (tm) tm->begin(sPanel);
-                    launch_gemm(g, sPanel);
-                    if (tm) tm->end(sPanel, FgpTimers::TRSM, 0.0);
-                }
+            GemmArgs g = base;
+            g.A = t.M + (long)k0 * t.ld;
+            g.B = t.W + (long)kk * NBk * NBk; g.ldb = NBk; g.strideB = t.strideW;
+            g.C = t.M + (long)k0 * t.ld;
+            g.K = nb; g.accumulate = 0;
+            g.tri0 = 0; g.triT = 0;
+            int tlo1 = S.lo1, thi1 = S.hi1;
+            if (fresh && nb < NBk && (long)k0 + nb < (long)std::min(t.nrows, (kk + 1) * NBk)) {
+                if (thi1 > tlo1) tlo1 = kk; else { tlo1 = kk; thi1 = kk + 1; }
             }
-            // -- update of the panel's remaining columns
-            if (kk + 1 < kend) {
-                GemmArgs g = make_update(kk, nb, S, kk + 1, kend);
+            g.rectR0 = tlo1; g.rectNR = thi1 - tlo1; g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2;
+            g.rectC0 = kk; g.rectNC = 1; g.bTileBase = kk;
+            g.rowMin = k0 + nb;
+            g.colMin = 0; g.colLo = nb; g.colHoleHi = nb; g.ncols = nb;
+            if (g.rectNR + g.rectNR1 > 0) {
                 if (tm) tm->begin(sPanel);
                 launch_gemm(g, sPanel);
-                if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
+                if (tm) tm->end(sPanel, FgpTimers::TRSM, 0.0);
             }
-        }
+        };
+        factor_range(k, kend);
         // ---- trailing update with the whole panel
         if (kend < ncT && Kpanel > 0) {
             const RowSet S = rows_of(kend - 1);

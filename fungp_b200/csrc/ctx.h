@@ -55,6 +55,28 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// caching device allocator (per context and device): cudaFree synchronises the whole device, which stalls every other
+// worker context of fgp_fit_batch; problems are created and destroyed per candidate, so their blocks are recycled
+struct DevPool {
+    struct Blk { void* p; size_t cap; bool used; };
+    std::vector<Blk> blks;
+    void* get(size_t bytes) {
+        bytes = std::max<size_t>(bytes, 256);
+        int best = -1;
+        for (int i = 0; i < (int)blks.size(); ++i)
+            if (!blks[i].used && blks[i].cap >= bytes && (best < 0 || blks[i].cap < blks[best].cap)) best = i;
+        if (best >= 0 && blks[best].cap <= 2 * bytes + 4096) { blks[best].used = true; return blks[best].p; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        blks.push_back({p, bytes, true});
+        return p;
+    }
+    void put(void* p) {
+        for (auto& b : blks) if (b.p == p) { b.used = false; return; }
+    }
+    void release() { for (auto& b : blks) cudaFree(b.p); blks.clear(); }
+};
+
 struct DevState {
     int device = 0;
     static const int MAXSTREAMS = 8;
@@ -65,6 +87,7 @@ struct DevState {
     DevBuf wbuf;      // inverse diagonal blocks
     DevBuf small;     // thetas / scales / results
     DevBuf aux;       // new-point coordinates etc.
+    DevPool pool;     // per-problem blocks (coordinates, y, stored factor)
     void* pinned = nullptr; size_t pinnedCap = 0;
     FgpTimers timers;
     double lastAsmMs = 0, lastFactorMs = 0;
@@ -77,8 +100,9 @@ struct fgp_ctx {
     int profile = 0;
     int lookahead = 1;
     int streams = 4;
-    int fit_workers = 4;      // fgp_fit_batch: concurrent candidate fits per GPU
-    int outer = 4;            // column tiles per outer panel (trailing update K = outer*128)
+    int fit_workers = 6;      // fgp_fit_batch: concurrent candidate fits per GPU
+    int outer = 8;            // column tiles per outer panel for batches (trailing update K = outer*128)
+    int outer_single = 2;     // same for a single factorisation with look-ahead (its panel chain is exposed)
     double timing[8] = {0};
     std::mutex mu;
 };

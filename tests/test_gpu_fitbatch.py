@@ -54,7 +54,7 @@ def test_stored_search_logs(ctx, name):
 def test_fit_batch_vs_host_mirror_and_worker_independence(ctx):
     from fungp_b200 import factory as F
     from fungp_b200 import model as M
-    n, ds, f_lens = 200, 3, [12, 20]
+    n, ds, f_lens = 640, 3, [12, 20]     # >= 512: the multi-stream path, with 4 concurrent worker contexts per GPU
     sIn, fIn, y, _ = synth_problem(91, n, ds, f_lens)
     rng = np.random.default_rng(4)
     ants = []

@@ -47,12 +47,12 @@ def run(n, B, streams, lookahead, ker="gauss", reps=3, profile=False, outer=4):
 
 recs = []
 for n in (1024, 2048, 4096, 8192):
-    for outer in (1, 2, 4):
+    for outer in (2, 4, 8):
         recs.append(run(n, 1, 1, 1, outer=outer))
-    recs.append(run(n, 1, 1, 0, profile=True, outer=1))
+    recs.append(run(n, 1, 1, 0, profile=True, outer=8))
     recs.append(run(n, 1, 1, 0, profile=True, outer=4))
 for n, B in ((1024, 64), (2048, 20), (8192, 8)):
-    for outer in (1, 2, 4):
+    for outer in (2, 4, 8):
         recs.append(run(n, B, 4, 0, outer=outer))
 out["runs"] = recs
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
