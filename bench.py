@@ -23,7 +23,6 @@ torch.distributed is used for the barrier and the max over ranks only.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -44,50 +43,57 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons / power during the timed region (B200_PROFILING.md recipe), sampled in-process through
+    NVML every 250 ms (spawning nvidia-smi -lms next to the timed loop perturbs kernel launches)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
         except Exception:
-            self.proc = None
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _run(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.25)
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if self.nvml is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable"])
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm = [x[0] for x in self.samples]; pw = [x[2] for x in self.samples]
         busy = [c for c, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
-        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
-                    power_w_max=float(max(pw)))
+        reasons = sorted({name for (_, _, _, rs) in self.samples for bit, name in self.REASONS.items() if rs & bit})
+        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(x[1] for x in self.samples)), reasons=reasons,
+                    samples=len(sm), power_w_max=float(max(pw)))
 
 
 FACTORY = dict(n=1024, ds=5, f_lens=[10, 22, 50], seed=1024, n_starts=1, n_presample=20, nugget=1e-8)
@@ -395,8 +401,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=4)
-    ap.add_argument("--outer", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--outer", type=int, default=16)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--factory-cands", type=int, default=48, help="candidate structures per GPU for the factory metric (0 = skip)")
     args = ap.parse_args()

@@ -99,9 +99,9 @@ struct fgp_ctx {
     std::string err;
     int profile = 0;
     int lookahead = 1;
-    int streams = 4;
+    int streams = 8;
     int fit_workers = 6;      // fgp_fit_batch: concurrent candidate fits per GPU
-    int outer = 8;            // column tiles per outer panel for batches (trailing update K = outer*128)
+    int outer = 16;           // column tiles per outer panel for batches (trailing update K = outer*128)
     int outer_single = 2;     // same for a single factorisation with look-ahead (its panel chain is exposed)
     double timing[8] = {0};
     std::mutex mu;

@@ -13,7 +13,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&M, sizeof(double) * ld * n);
     cudaMemset(M, 0, sizeof(double) * ld * n);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int K : {128, 256, 512}) for (int dbg : {0, 1, 2, 3, 4, 7, 8, 15, 16}) {
+    for (int K : {128, 256, 512, 1024, 2048}) for (int dbg : {0, 32, 1, 3, 16}) {
         GemmArgs g{};
         g.A = M; g.B = M; g.C = M; g.lda = g.ldb = g.ldc = ld; g.K = K; g.accumulate = 1;
         g.tri0 = 4; g.triT = T; g.rowLo = n; g.rowHoleHi = n; g.nrows = n; g.colLo = n; g.colHoleHi = n; g.ncols = n;
