@@ -39,6 +39,9 @@ SIGNATURES = {
     "fgp_fit_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_dpp, c_dp, C.c_int, c_ip,
                                 C.c_double, C.c_int, C.c_int, c_dp, C.POINTER(C.c_longlong), C.c_int, c_dp, c_dp,
                                 c_dp, c_dp, c_ip]),
+    "fgp_fit_batch_holdout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_dpp, c_dp, C.c_int, c_ip,
+                                        C.c_double, C.c_int, C.c_int, c_dp, C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int,
+                                        c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "fgp_get_timing": (C.c_int, [C.c_void_p, c_dp]),
     "fgp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "fgp_launch_count": (C.c_longlong, []),

@@ -105,10 +105,11 @@ class Context:
         self.check(self.lib.fgp_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(c)), "fgp_measure_peaks")
         return dict(dmma_tflops=a.value, dfma_tflops=b.value, copy_gbs=c.value)
 
-    def fit_batch(self, sIn, fIn, y, ants, u01, nugget=1e-8, n_starts=1, n_presample=20, dmax=None):
-        """fgp_fit_batch: score candidate structures (rows of `ants`, wire format of formatSol_ACO).
-        u01: list with one array per candidate (d_c * max(n_presample, n_starts) uniform draws, column-major d_c x n).
-        -> dict(fitness, nll, sig2, theta (n_cand x dmax), info)"""
+    def fit_batch(self, sIn, fIn, y, ants, u01, nugget=1e-8, n_starts=1, n_presample=20, dmax=None, ind_vl=None):
+        """fgp_fit_batch / fgp_fit_batch_holdout: score candidate structures (rows of `ants`, wire format of formatSol_ACO).
+        u01: list with one array per work item (d_c * max(n_presample, n_starts) uniform draws, column-major d_c x n);
+        work items = candidates, or (candidate, replicate) pairs, candidate-major, when ind_vl (n_vl x n_rep, 1-based) is given.
+        -> dict(fitness, nll, sig2, theta (items x dmax), info)"""
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel())
         n = y.size
         s = None if sIn is None else _f(np.asarray(sIn, dtype=np.float64).reshape(n, -1))
@@ -116,7 +117,13 @@ class Context:
         fs = [_f(f) for f in (fIn or [])]
         df = len(fs)
         ants = np.ascontiguousarray(np.asarray(ants, dtype=np.int32).reshape(-1, ds + 4 * df + 1))
-        nc = ants.shape[0]
+        ncand = ants.shape[0]
+        iv = None
+        n_rep = 0
+        if ind_vl is not None:
+            iv = np.asfortranarray(np.asarray(ind_vl, dtype=np.int32).reshape(len(ind_vl), -1))
+            n_rep = iv.shape[1]
+        nc = ncand * max(1, n_rep)
         off = np.zeros(nc, dtype=np.int64)
         flat = []
         pos = 0
@@ -129,10 +136,13 @@ class Context:
             dmax = ds + sum(f.shape[1] for f in fs)
         k = (C.c_int * max(1, df))(*[f.shape[1] for f in fs])
         fit = np.zeros(nc); nll = np.zeros(nc); s2 = np.zeros(nc); th = np.zeros((nc, dmax)); info = np.zeros(nc, dtype=np.int32)
-        rc = self.lib.fgp_fit_batch(self.h, n, ds, None if s is None else _dp(s), df, k, _dpp(fs), _dp(y), nc,
-                                    ants.ctypes.data_as(_lib.c_ip), float(nugget), int(n_starts), int(n_presample), _dp(flat),
-                                    off.ctypes.data_as(C.POINTER(C.c_longlong)), int(dmax), _dp(fit), _dp(nll), _dp(s2), _dp(th),
-                                    info.ctypes.data_as(_lib.c_ip))
+        common = (self.h, n, ds, None if s is None else _dp(s), df, k, _dpp(fs), _dp(y), ncand, ants.ctypes.data_as(_lib.c_ip),
+                  float(nugget), int(n_starts), int(n_presample), _dp(flat), off.ctypes.data_as(C.POINTER(C.c_longlong)), int(dmax))
+        outs = (_dp(fit), _dp(nll), _dp(s2), _dp(th), info.ctypes.data_as(_lib.c_ip))
+        if iv is None:
+            rc = self.lib.fgp_fit_batch(*common, *outs)
+        else:
+            rc = self.lib.fgp_fit_batch_holdout(*common, n_rep, iv.shape[0], iv.ctypes.data_as(_lib.c_ip), *outs)
         self.check(rc, "fgp_fit_batch")
         return dict(fitness=fit, nll=nll, sig2=s2, theta=th, info=info)
 

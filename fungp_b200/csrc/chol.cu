@@ -48,6 +48,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     base.rowMin = 0; base.rowLo = t.holeLo; base.rowHoleHi = t.holeHi; base.nrows = t.nrows;
     base.colMin = 0; base.colLo = t.colHoleLo; base.colHoleHi = t.colHoleHi; base.ncols = t.ncols;
     base.batch = t.batch;
+    base.maxTilesPerCta = la_pre ? 1 : 0;
 
     cudaEvent_t evPanel = nullptr, evBulk = nullptr;
     const bool la = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;

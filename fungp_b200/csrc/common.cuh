@@ -108,6 +108,7 @@ struct GemmArgs {
     int rowMin, rowLo, rowHoleHi, nrows;       // valid r: r >= rowMin && (r < rowLo || (rowHoleHi <= r < nrows))
     int colMin, colLo, colHoleHi, ncols;       // same for c
     int batch;
+    int maxTilesPerCta;                        // 0 = automatic; 1 = one tile per CTA (look-ahead: the panel stream must find a free SM quickly)
     int dbg;                                   // experiment switches, honoured only when built with -DFGP_GEMM_DEBUG
 };
 void launch_gemm(const GemmArgs& g, cudaStream_t st);

@@ -18,7 +18,7 @@
 
 namespace {
 
-struct Proj { std::vector<double> B, J, coefs; int pe = 0; bool ok = false; };
+struct Proj { std::vector<double> B, J, coefs, coefsVl; int pe = 0; bool ok = false; };
 
 struct Shared {
     int n, ds, df;
@@ -27,22 +27,47 @@ struct Shared {
     double nugget; int n_starts, n_presample;
     const double* u01; const long long* u01_off; int dmax;
     double *fitness, *nll, *sig2, *theta; int* info;
+    // hold-out validation (eval_houtv_ACO): n_rep splits, n_vl validation rows each (1-based row indices, column-major
+    // n_vl x n_rep); n_rep = 0 -> leave-one-out fitness on the full data
+    int n_rep = 0, n_vl = 0; const int* ind_vl = nullptr;
+    std::vector<std::vector<int>> trRows, vlRows;       // per replicate: 0-based training / validation rows
+    std::vector<std::vector<double>> yTr, yVl;
     std::mutex mu;
-    std::map<std::tuple<int, int, int>, Proj> cache;    // (input, p, basis) -> projection, shared by all candidates
+    std::map<std::tuple<int, int, int, int>, Proj> cache;    // (input, p, basis, replicate) -> projection, shared by all items
     std::atomic<int> next{0};
     std::atomic<int> failures{0};
 };
 
-const Proj& projection(Shared& S, int j, int p, int basis) {
+// gather rows of a column-major n x k matrix
+std::vector<double> take_rows(const double* M, int n, int k, const std::vector<int>& rows) {
+    std::vector<double> out((size_t)rows.size() * k);
+    for (int c = 0; c < k; ++c)
+        for (size_t r = 0; r < rows.size(); ++r) out[r + (size_t)c * rows.size()] = M[rows[r] + (size_t)c * n];
+    return out;
+}
+
+// dimReduction of input j on the training rows of replicate `rep` (-1: all rows) and, for a hold-out split, the
+// projection of the validation curves with the same basis (R/1_fgpm_Class.R:844-845)
+const Proj& projection(Shared& S, int j, int p, int basis, int rep) {
     std::lock_guard<std::mutex> lk(S.mu);
-    auto key = std::make_tuple(j, p, basis);
+    auto key = std::make_tuple(j, p, basis, rep);
     auto it = S.cache.find(key);
     if (it != S.cache.end()) return it->second;
     Proj pr;
     const int kk = S.k[j];
     pr.pe = p ? p : kk;
-    pr.B.resize((size_t)kk * pr.pe); pr.J.resize((size_t)pr.pe * pr.pe); pr.coefs.resize((size_t)S.n * pr.pe);
-    pr.ok = fgp_project(nullptr, S.fIn[j], S.n, kk, p, basis, nullptr, pr.B.data(), pr.J.data(), pr.coefs.data()) == 0;
+    pr.B.resize((size_t)kk * pr.pe); pr.J.resize((size_t)pr.pe * pr.pe);
+    if (rep < 0) {
+        pr.coefs.resize((size_t)S.n * pr.pe);
+        pr.ok = fgp_project(nullptr, S.fIn[j], S.n, kk, p, basis, nullptr, pr.B.data(), pr.J.data(), pr.coefs.data()) == 0;
+    } else {
+        const std::vector<double> ftr = take_rows(S.fIn[j], S.n, kk, S.trRows[rep]), fvl = take_rows(S.fIn[j], S.n, kk, S.vlRows[rep]);
+        const int ntr = (int)S.trRows[rep].size(), nvl = (int)S.vlRows[rep].size();
+        pr.coefs.resize((size_t)ntr * pr.pe); pr.coefsVl.resize((size_t)nvl * pr.pe);
+        std::vector<double> Jtmp((size_t)pr.pe * pr.pe), Btmp((size_t)kk * pr.pe);
+        pr.ok = fgp_project(nullptr, ftr.data(), ntr, kk, p, basis, nullptr, pr.B.data(), pr.J.data(), pr.coefs.data()) == 0 &&
+                fgp_project(nullptr, fvl.data(), nvl, kk, p, basis, p ? pr.B.data() : nullptr, Btmp.data(), Jtmp.data(), pr.coefsVl.data()) == 0;
+    }
     return S.cache.emplace(key, std::move(pr)).first->second;
 }
 
@@ -52,16 +77,26 @@ void crash(Shared& S, int c, int code) {
     S.info[c] = code;
 }
 
-void fit_one(Shared& S, fgp_ctx* ctx, int c) {
-    const int* ant = S.ants + (size_t)c * S.antLen;
+void fit_one(Shared& S, fgp_ctx* ctx, int item) {
+    const int nrep = std::max(1, S.n_rep);
+    const int cand = item / nrep, rep = S.n_rep > 0 ? item % nrep : -1;
+    const int c = item;                 // output slot
+    const int* ant = S.ants + (size_t)cand * S.antLen;
+    const int n = rep < 0 ? S.n : (int)S.trRows[rep].size();
+    const double* yv = rep < 0 ? S.y : S.yTr[rep].data();
     // ---- formatSol_ACO
-    std::vector<double> sAct;
+    std::vector<double> sAct, sVl;
     int dsA = 0;
     for (int i = 0; i < S.ds; ++i)
         if (ant[i] == 1) {
-            sAct.insert(sAct.end(), S.sIn + (size_t)i * S.n, S.sIn + (size_t)(i + 1) * S.n);
+            if (rep < 0) sAct.insert(sAct.end(), S.sIn + (size_t)i * S.n, S.sIn + (size_t)(i + 1) * S.n);
+            else {
+                for (int r : S.trRows[rep]) sAct.push_back(S.sIn[r + (size_t)i * S.n]);
+                for (int r : S.vlRows[rep]) sVl.push_back(S.sIn[r + (size_t)i * S.n]);
+            }
             ++dsA;
         }
+    std::vector<const double*> coefsVl;
     std::vector<const double*> coefs, Js;
     std::vector<int> p, dis;
     for (int j = 0; j < S.df; ++j) {
@@ -69,16 +104,17 @@ void fit_one(Shared& S, fgp_ctx* ctx, int c) {
         if (a[0] != 1) continue;
         const int dist = a[1], dim = a[2], bas = (a[3] == FGP_BASIS_PCA) ? FGP_BASIS_PCA : FGP_BASIS_BSPLINES;
         if ((dist != FGP_DIST_BYGROUP && dist != FGP_DIST_BYINDEX) || dim < 0 || dim > S.k[j]) { crash(S, c, -1); return; }
-        const Proj& pr = projection(S, j, dim, bas);
+        const Proj& pr = projection(S, j, dim, bas, rep);
         if (!pr.ok) { crash(S, c, -2); return; }
         coefs.push_back(pr.coefs.data()); Js.push_back(pr.J.data()); p.push_back(pr.pe); dis.push_back(dist);
+        coefsVl.push_back(pr.coefsVl.data());
     }
     const int ker = ant[S.antLen - 1];
     const int dfA = (int)coefs.size();
     if ((dsA == 0 && dfA == 0) || ker < 1 || ker > 3) { crash(S, c, -1); return; }
 
     fgp_problem* P = nullptr;
-    if (fgp_problem_create(ctx, S.n, dsA, dsA ? sAct.data() : nullptr, dfA, p.data(), dis.data(), coefs.data(), Js.data(), S.y, &P)) {
+    if (fgp_problem_create(ctx, n, dsA, dsA ? sAct.data() : nullptr, dfA, p.data(), dis.data(), coefs.data(), Js.data(), yv, &P)) {
         crash(S, c, -3); return;
     }
     const int d = fgp_problem_nls(P);
@@ -90,7 +126,7 @@ void fit_one(Shared& S, fgp_ctx* ctx, int c) {
     for (int i = 0; i < d; ++i) up[i] *= 2.0;
     // ---- setSPoints_*: the presample draws were made by the caller (R's runif, in ant order)
     const int npre = std::max(S.n_presample, S.n_starts);
-    const double* u = S.u01 + S.u01_off[c];
+    const double* u = S.u01 + S.u01_off[item];
     std::vector<double> pts((size_t)d * npre), v(npre), s2(npre);
     std::vector<int> inf(npre);
     for (int j = 0; j < npre; ++j)
@@ -137,8 +173,22 @@ void fit_one(Shared& S, fgp_ctx* ctx, int c) {
     int rc = fgp_premats(P, ker, S.nugget, s1, bestx.data(), nullptr, nullptr);
     if (rc) { done(rc); return; }
     double q2 = 0.0;
-    rc = fgp_loocv(P, nullptr, &q2);
-    if (rc) { done(rc); return; }
+    if (rep < 0) {
+        rc = fgp_loocv(P, nullptr, &q2);                       // Q2loocv (R/1_Xfgpm_Class.R:539-542)
+        if (rc) { done(rc); return; }
+    } else {
+        // Q2hout: predict the validation rows (R/1_Xfgpm_Class.R:545-549)
+        const int nvl = (int)S.vlRows[rep].size();
+        std::vector<double> mean(nvl), sd(nvl);
+        rc = fgp_predict(P, nvl, dsA ? sVl.data() : nullptr, coefsVl.data(), FGP_DETAIL_LIGHT, mean.data(), sd.data(), nullptr, nullptr);
+        if (rc) { done(rc); return; }
+        const std::vector<double>& yvl = S.yVl[rep];
+        double mu = 0.0, se = 0.0, st = 0.0;
+        for (int i = 0; i < nvl; ++i) mu += yvl[i];
+        mu /= nvl;
+        for (int i = 0; i < nvl; ++i) { se += (yvl[i] - mean[i]) * (yvl[i] - mean[i]); st += (yvl[i] - mu) * (yvl[i] - mu); }
+        q2 = 1.0 - (se / nvl) / (st / nvl);
+    }
     S.fitness[c] = q2; S.nll[c] = bestf; S.sig2[c] = s1; S.info[c] = 0;
     for (int i = 0; i < S.dmax; ++i) S.theta[(size_t)c * S.dmax + i] = i < d ? bestx[i] : std::nan("");
     done(0);
@@ -146,19 +196,36 @@ void fit_one(Shared& S, fgp_ctx* ctx, int c) {
 
 }  // namespace
 
-extern "C" int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
-                             const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
-                             const double* u01, const long long* u01_off, int dmax, double* fitness, double* nll,
-                             double* sig2, double* theta, int* info) {
+static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
+                          const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
+                          const double* u01, const long long* u01_off, int dmax, int n_rep, int n_vl, const int* ind_vl,
+                          double* fitness, double* nll, double* sig2, double* theta, int* info) {
     if (!ctx || n <= 0 || ds < 0 || df < 0 || (ds > 0 && !sIn) || (df > 0 && (!k || !fIn)) || !y || n_cand < 0 || !ants ||
         n_starts < 1 || n_presample < 1 || !u01 || !u01_off || dmax < 1 || !fitness || !nll || !sig2 || !theta || !info)
         return FGP_ERR_ARG;
+    if (n_rep < 0 || (n_rep > 0 && (n_vl < 1 || n_vl >= n || !ind_vl))) return FGP_ERR_ARG;
     Shared S;
     S.n = n; S.ds = ds; S.df = df; S.sIn = sIn; S.k = k; S.fIn = fIn; S.y = y;
     S.n_cand = n_cand; S.antLen = ds + 4 * df + 1; S.ants = ants;
     S.nugget = nugget; S.n_starts = n_starts; S.n_presample = n_presample;
     S.u01 = u01; S.u01_off = u01_off; S.dmax = dmax;
     S.fitness = fitness; S.nll = nll; S.sig2 = sig2; S.theta = theta; S.info = info;
+    S.n_rep = n_rep; S.n_vl = n_vl; S.ind_vl = ind_vl;
+    for (int r = 0; r < n_rep; ++r) {            // splitData (R/1_Xfgpm_Class.R:559-584)
+        std::vector<char> isvl(n, 0);
+        std::vector<int> vl, tr;
+        for (int i = 0; i < n_vl; ++i) {
+            const int idx = ind_vl[i + (size_t)r * n_vl] - 1;
+            if (idx < 0 || idx >= n) return FGP_ERR_ARG;
+            isvl[idx] = 1; vl.push_back(idx);
+        }
+        for (int i = 0; i < n; ++i) if (!isvl[i]) tr.push_back(i);
+        std::vector<double> ytr, yvl;
+        for (int i : tr) ytr.push_back(y[i]);
+        for (int i : vl) yvl.push_back(y[i]);
+        S.trRows.push_back(tr); S.vlRows.push_back(vl); S.yTr.push_back(ytr); S.yVl.push_back(yvl);
+    }
+    const int n_items = n_cand * std::max(1, n_rep);
     const int nd = (int)ctx->dev.size();
     const int wpd = std::max(1, ctx->fit_workers);
     std::vector<std::thread> th;
@@ -169,18 +236,36 @@ extern "C" int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int
             th.emplace_back([&, device]() {
                 fgp_ctx* wc = nullptr;
                 if (fgp_ctx_create(1, &device, &wc) != 0) { ctxFail++; return; }
-                wc->streams = ctx->streams; wc->outer = ctx->outer; wc->lookahead = ctx->lookahead;
+                wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
                 for (;;) {
-                    const int c = S.next.fetch_add(1);
-                    if (c >= S.n_cand) break;
-                    fit_one(S, wc, c);
+                    const int item = S.next.fetch_add(1);
+                    if (item >= n_items) break;
+                    fit_one(S, wc, item);
                 }
                 fgp_ctx_destroy(wc);
             });
         }
     for (auto& t : th) t.join();
     cudaSetDevice(ctx->dev[0].device);
-    if (ctxFail.load() == nd * wpd && n_cand > 0) { fgp_set_err(ctx, "fgp_fit_batch: no worker context could be created"); return FGP_ERR_CUDA; }
-    if (S.next.load() < S.n_cand) { fgp_set_err(ctx, "fgp_fit_batch: workers stopped early"); return FGP_ERR_CUDA; }
+    if (ctxFail.load() == nd * wpd && n_items > 0) { fgp_set_err(ctx, "fgp_fit_batch: no worker context could be created"); return FGP_ERR_CUDA; }
+    if (S.next.load() < n_items) { fgp_set_err(ctx, "fgp_fit_batch: workers stopped early"); return FGP_ERR_CUDA; }
     return 0;
+}
+
+extern "C" int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
+                             const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
+                             const double* u01, const long long* u01_off, int dmax, double* fitness, double* nll,
+                             double* sig2, double* theta, int* info) {
+    return fit_batch_impl(ctx, n, ds, sIn, df, k, fIn, y, n_cand, ants, nugget, n_starts, n_presample, u01, u01_off, dmax, 0, 0,
+                          nullptr, fitness, nll, sig2, theta, info);
+}
+
+extern "C" int fgp_fit_batch_holdout(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k,
+                                     const double* const* fIn, const double* y, int n_cand, const int* ants, double nugget,
+                                     int n_starts, int n_presample, const double* u01, const long long* u01_off, int dmax,
+                                     int n_rep, int n_vl, const int* ind_vl, double* fitness, double* nll, double* sig2,
+                                     double* theta, int* info) {
+    if (n_rep < 1) return FGP_ERR_ARG;
+    return fit_batch_impl(ctx, n, ds, sIn, df, k, fIn, y, n_cand, ants, nugget, n_starts, n_presample, u01, u01_off, dmax, n_rep,
+                          n_vl, ind_vl, fitness, nll, sig2, theta, info);
 }

@@ -376,8 +376,9 @@ void launch_gemm(const GemmArgs& g, cudaStream_t st) {
     // semi-persistent: a CTA walks several tiles (operand prefetch across tile boundaries), but holds its SM for at
     // most ~0.4 ms so that other streams' panel kernels (diagonal block, panel solve) get an SM quickly
     const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
-    const int tpc = std::max(1, std::min(16, 3072 / std::max(1, g.K)));       // tiles per CTA: K=128 -> 16 ... K>=2048 -> 1
-    int gx = std::max(std::min(ntiles, sms), (ntiles + tpc - 1) / tpc);
+    int tpc = std::max(1, std::min(16, 3072 / std::max(1, g.K)));       // tiles per CTA: K=128 -> 16 ... K>=2048 -> 1
+    if (g.maxTilesPerCta > 0) tpc = std::min(tpc, g.maxTilesPerCta);
+    int gx = g.maxTilesPerCta == 1 ? ntiles : std::max(std::min(ntiles, sms), (ntiles + tpc - 1) / tpc);
     if (g.dbg & 32) gx = ntiles;
     dim3 grid(gx, g.batch);
     FGP_COUNT_LAUNCH();

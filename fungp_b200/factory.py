@@ -99,13 +99,21 @@ def parse_call_string(call, ds, df):
     return encode_ant(ds, df, s_active, f_active, dis, pd, bas, ker)
 
 
-def score_candidates(ctx, sIn, fIn, sOut, ants, rng, nugget=1e-8, n_starts=1, n_presample=20):
-    """eval_loocv_ACO for a whole generation: the presample draws are taken from `rng.runif` in ant order (as the
-    sequential reference loop would consume them), then every ant is fitted and scored on the GPU(s)."""
+def score_candidates(ctx, sIn, fIn, sOut, ants, rng, nugget=1e-8, n_starts=1, n_presample=20, ind_vl=None):
+    """eval_loocv_ACO (ind_vl None) / eval_houtv_ACO (ind_vl = n_vl x n_rep matrix of 1-based validation rows) for a
+    whole generation: the presample draws are taken from `rng.runif` in ant (and replicate) order, as the sequential
+    reference loop would consume them, then every work item is fitted and scored on the GPU(s).  With hold-out the
+    result additionally has `fitness_mean` = mean over the replicates that did not crash (R/3_ant_admin.R:719-721)."""
     ants = np.asarray(ants, dtype=np.int32)
     ds = 0 if sIn is None else np.asarray(sIn).reshape(len(sOut), -1).shape[1]
     df = len(fIn or [])
     k = [np.asarray(f).shape[1] for f in (fIn or [])]
     npre = max(n_presample, n_starts)
-    u01 = [np.asarray(rng.runif(n_lengthscales(a, ds, df, k) * npre)) for a in ants]
-    return ctx.fit_batch(sIn, fIn, sOut, ants, u01, nugget=nugget, n_starts=n_starts, n_presample=n_presample)
+    n_rep = 1 if ind_vl is None else np.asarray(ind_vl).reshape(len(ind_vl), -1).shape[1]
+    u01 = [np.asarray(rng.runif(n_lengthscales(a, ds, df, k) * npre)) for a in ants for _ in range(n_rep)]
+    res = ctx.fit_batch(sIn, fIn, sOut, ants, u01, nugget=nugget, n_starts=n_starts, n_presample=n_presample, ind_vl=ind_vl)
+    if ind_vl is not None:
+        f = res["fitness"].reshape(len(ants), n_rep)
+        with np.errstate(invalid="ignore"):
+            res["fitness_mean"] = np.array([np.nanmean(r) if np.any(np.isfinite(r)) else np.nan for r in f])
+    return res

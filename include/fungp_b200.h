@@ -127,6 +127,17 @@ int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const 
                   const double* u01, const long long* u01_off, int dmax, double* fitness, double* nll, double* sig2,
                   double* theta, int* info);
 
+/* eval_houtv_ACO (R/3_ant_admin.R:662-802): the same with hold-out validation.  ind_vl is n_vl x n_rep (column-major,
+ * 1-based row indices as in R's ind.vl matrix); every (candidate, replicate) pair is one work item: the model is fitted
+ * on the rows not in column j (splitData, R/1_Xfgpm_Class.R:559-584; the projection basis is built from the training
+ * rows) and scored with Q2hout = 1 - mean((y.vl - predict(model)$mean)^2) / mean((y.vl - mean(y.vl))^2)
+ * (R/1_Xfgpm_Class.R:545-549).  Outputs and u01 offsets are per work item, candidate-major: item = c * n_rep + j.
+ * Averaging over replicates and crash handling stay with the caller (R/3_ant_admin.R:712-728). */
+int fgp_fit_batch_holdout(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
+                          const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
+                          const double* u01, const long long* u01_off, int dmax, int n_rep, int n_vl, const int* ind_vl,
+                          double* fitness, double* nll, double* sig2, double* theta, int* info);
+
 /* ---- instrumentation ------------------------------------------------------------------------------- */
 /* timing of the last call on device 0 (CUDA events on the library's own streams), milliseconds / counts:
  *  [0] assembly kernel ms  [1] factorisation (all launches) ms  [2] trailing-update (DMMA) kernel ms summed

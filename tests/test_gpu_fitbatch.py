@@ -95,3 +95,37 @@ def test_fit_batch_vs_host_mirror_and_worker_independence(ctx):
             agree += 1
             assert abs(q2 - r4["fitness"][c]) <= 1e-3, (c, q2, r4["fitness"][c])
     assert agree >= 0.8 * len(ants), agree
+
+
+def test_holdout_fitness_vs_host_mirror(ctx):
+    """eval_houtv_ACO: fit on the training split, Q2hout on the validation rows, two replicates -- against the host
+    mirror (fgpm + predict on the same split, same presample stream)."""
+    from fungp_b200 import factory as F
+    from fungp_b200 import model as M
+    n, ds = 240, 2
+    sIn, fIn, y, _ = synth_problem(93, n, ds, [14, 18])
+    rng = np.random.default_rng(2)
+    ind_vl = np.stack([np.sort(rng.choice(n, 48, replace=False)) + 1 for _ in range(2)], axis=1)      # 48 x 2, 1-based
+    ants = np.stack([F.encode_ant(ds, 2, [0, 1], [0, 1], ["L2_bygroup", "L2_byindex"], [3, 2], ["B-splines", "PCA"], "matern5_2"),
+                     F.encode_ant(ds, 2, [1], [1], ["L2_bygroup"], [4], ["PCA"], "gauss"),
+                     F.encode_ant(ds, 2, [0, 1], [], [], [], [], "matern3_2")])
+    res = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20, ind_vl=ind_vl)
+    assert res["fitness"].shape == (6,) and (res["info"] == 0).all()
+    rr = RRng(3)
+    for c, ant in enumerate(ants):
+        kw = F.decode_ant(ant, ds, 2)
+        for j in range(2):
+            vl = ind_vl[:, j] - 1
+            tr = np.setdiff1d(np.arange(n), vl)
+            m = M.fgpm(sIn=sIn[np.ix_(tr, kw["s_active"])] if kw["s_active"] else None,
+                       fIn=[fIn[q][tr] for q in kw["f_active"]] if kw["f_active"] else None, sOut=y[tr], kerType=kw["kerType"],
+                       f_disType=kw["f_disType"] or "L2_bygroup", f_pdims=kw["f_pdims"] or 3, f_basType=kw["f_basType"] or "B-splines",
+                       n_starts=2, n_presample=20, rng=rr, ctx=ctx, want_L=False)
+            pr = M.predict(m, sIn_pr=sIn[np.ix_(vl, kw["s_active"])] if kw["s_active"] else None,
+                           fIn_pr=[fIn[q][vl] for q in kw["f_active"]] if kw["f_active"] else None)
+            q2 = 1.0 - np.mean((y[vl] - pr["mean"]) ** 2) / np.mean((y[vl] - np.mean(y[vl])) ** 2)
+            m.close()
+            item = c * 2 + j
+            if abs(m.negLogLik - res["nll"][item]) <= 1e-5 * max(1.0, abs(m.negLogLik)):
+                assert abs(q2 - res["fitness"][item]) <= 2e-3, (item, q2, res["fitness"][item])
+    assert np.all(np.isfinite(res["fitness_mean"]))
