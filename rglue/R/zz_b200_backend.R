@@ -101,3 +101,18 @@ makeSims_B200 <- function(prob, sIn.sm, coefs.sm, n.sm, nsim, nugget.sm, detail,
 
 # getOut_loocv (R/8_outilsStats.R:1-7): same return value (n x 1 matrix of leave-one-out predictions)
 getOut_loocv <- function(model) .Call(fgpR_loocv, model@b200prob)[[1]]
+
+# eval_loocv_ACO / eval_houtv_ACO (R/3_ant_admin.R:592-648, 662-802): one device call per generation.  The presample
+# uniforms are drawn HERE, in ant (and replicate) order, exactly as the sequential loop over fitNtests_ACO -> fgpm ->
+# setSPoints_* would draw them (runif(n.ls * n.presample) per fit, R/3_training_SF.R:91), so R's RNG stream -- and with
+# it the ants the colony builds next -- is unchanged.  n.ls per ant comes from its structure (getOwners).
+eval_ACO_B200 <- function(sIn, fIn, sOut, extargs, ants, n.ls, ind.vl = NULL) {
+  n.rep <- if (is.null(ind.vl)) 1L else ncol(ind.vl)
+  n.pre <- max(extargs$n.presample, extargs$n.starts)
+  sizes <- rep(n.ls * n.pre, each = n.rep)
+  u01 <- runif(sum(sizes))
+  r <- .Call(fgpR_fit_batch, b200_ctx(), sIn, fIn, as.numeric(sOut), t(ants), extargs$nugget, as.integer(extargs$n.starts),
+             as.integer(extargs$n.presample), u01, as.numeric(c(0, cumsum(sizes))[seq_along(sizes)]), as.integer(max(n.ls)), ind.vl)
+  fitness <- matrix(r[[1]], nrow = n.rep)                       # NaN = crashed fit (logged as a crash, fitness NA)
+  list(fitness = apply(fitness, 2, function(v) if (all(is.nan(v))) NA else mean(v[!is.nan(v)])), nll = r[[2]], hypers = r[[4]])
+}

@@ -200,3 +200,39 @@ SEXP fgpR_set_y(SEXP prob, SEXP y) {
     check(fgp_problem_set_y(get_prob(prob), REAL(y)), NULL, "set_y");
     return R_NilValue;
 }
+
+/* eval_loocv_ACO / eval_houtv_ACO for one generation (R/3_ant_admin.R:592-648, 662-802):
+ * .Call(fgpR_fit_batch, ctx, sIn_or_NULL, fIn(list of n x k_j matrices), sOut, t(ants) (integer, one candidate per COLUMN so
+ *       that each candidate is contiguous), nugget, n.starts, n.presample, u01 (the runif draws, concatenated per work item),
+ *       u01_off (numeric offsets, one per work item), dmax, ind.vl_or_NULL (integer n.vl x n.rep))
+ * -> list(fitness, nll, sig2, theta (dmax x items), info); items = ants, or (ant, replicate) pairs ant-major. */
+SEXP fgpR_fit_batch(SEXP ctx, SEXP sIn, SEXP fIn, SEXP sOut, SEXP antsT, SEXP nugget, SEXP n_starts, SEXP n_presample, SEXP u01,
+                    SEXP u01_off, SEXP dmax_, SEXP ind_vl) {
+    const int n = Rf_length(sOut), ds = Rf_isNull(sIn) ? 0 : Rf_ncols(sIn), df = Rf_length(fIn);
+    const int n_cand = Rf_ncols(antsT), dmax = Rf_asInteger(dmax_);
+    const int n_rep = Rf_isNull(ind_vl) ? 0 : Rf_ncols(ind_vl), n_vl = Rf_isNull(ind_vl) ? 0 : Rf_nrows(ind_vl);
+    const int items = n_cand * (n_rep > 0 ? n_rep : 1);
+    const double* fp[64]; int k[64]; long long off[4096];
+    if (df > 64) Rf_error("funGp: more than 64 functional inputs");
+    if (items > 4096 || Rf_length(u01_off) != items) Rf_error("funGp: u01_off must have one entry per work item (<= 4096)");
+    for (int j = 0; j < df; ++j) { fp[j] = REAL(VECTOR_ELT(fIn, j)); k[j] = Rf_ncols(VECTOR_ELT(fIn, j)); }
+    for (int i = 0; i < items; ++i) off[i] = (long long)REAL(u01_off)[i];
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
+    SEXP fit = PROTECT(Rf_allocVector(REALSXP, items)), nll = PROTECT(Rf_allocVector(REALSXP, items));
+    SEXP s2 = PROTECT(Rf_allocVector(REALSXP, items)), th = PROTECT(Rf_allocMatrix(REALSXP, dmax, items));
+    SEXP info = PROTECT(Rf_allocVector(INTSXP, items));
+    int rc;
+    if (n_rep == 0)
+        rc = fgp_fit_batch(get_ctx(ctx), n, ds, ds ? REAL(sIn) : NULL, df, k, fp, REAL(sOut), n_cand, INTEGER(antsT), Rf_asReal(nugget),
+                           Rf_asInteger(n_starts), Rf_asInteger(n_presample), REAL(u01), off, dmax, REAL(fit), REAL(nll), REAL(s2),
+                           REAL(th), INTEGER(info));
+    else
+        rc = fgp_fit_batch_holdout(get_ctx(ctx), n, ds, ds ? REAL(sIn) : NULL, df, k, fp, REAL(sOut), n_cand, INTEGER(antsT),
+                                   Rf_asReal(nugget), Rf_asInteger(n_starts), Rf_asInteger(n_presample), REAL(u01), off, dmax, n_rep,
+                                   n_vl, INTEGER(ind_vl), REAL(fit), REAL(nll), REAL(s2), REAL(th), INTEGER(info));
+    check(rc, get_ctx(ctx), "fit_batch");
+    SET_VECTOR_ELT(out, 0, fit); SET_VECTOR_ELT(out, 1, nll); SET_VECTOR_ELT(out, 2, s2); SET_VECTOR_ELT(out, 3, th);
+    SET_VECTOR_ELT(out, 4, info);
+    UNPROTECT(6);
+    return out;
+}

@@ -15,6 +15,7 @@ extern SEXP fgpR_predict(SEXP, SEXP, SEXP, SEXP, SEXP);
 extern SEXP fgpR_simulate(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 extern SEXP fgpR_loocv(SEXP);
 extern SEXP fgpR_set_y(SEXP, SEXP);
+extern SEXP fgpR_fit_batch(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 static const R_CallMethodDef CallEntries[] = {
     {"fgpR_ctx_create", (DL_FUNC)&fgpR_ctx_create, 1},       {"fgpR_project", (DL_FUNC)&fgpR_project, 5},
@@ -23,6 +24,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"fgpR_nll_batch", (DL_FUNC)&fgpR_nll_batch, 5},         {"fgpR_premats", (DL_FUNC)&fgpR_premats, 5},
     {"fgpR_predict", (DL_FUNC)&fgpR_predict, 5},             {"fgpR_simulate", (DL_FUNC)&fgpR_simulate, 6},
     {"fgpR_loocv", (DL_FUNC)&fgpR_loocv, 1},                 {"fgpR_set_y", (DL_FUNC)&fgpR_set_y, 2},
+    {"fgpR_fit_batch", (DL_FUNC)&fgpR_fit_batch, 12},
     {NULL, NULL, 0}};
 
 void R_init_funGp(DllInfo* dll) {

@@ -25,7 +25,7 @@ def test_glue_uses_only_declared_c_abi_and_registers_all_wrappers():
     wrappers = set(re.findall(r"^SEXP (fgpR_[a-z0-9_]+)\(", glue_nc, flags=re.M))
     init = open(os.path.join(G, "init.c")).read()
     registered = set(re.findall(r'\{"(fgpR_[a-z0-9_]+)"', init))
-    assert wrappers == registered and len(wrappers) >= 12
+    assert wrappers == registered and len(wrappers) >= 13
     rfile = open(os.path.join(G, "R", "zz_b200_backend.R")).read()
     called = set(re.findall(r"\.Call\((fgpR_[a-z0-9_]+)", rfile))
     assert called <= wrappers, called - wrappers
