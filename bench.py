@@ -122,15 +122,14 @@ def factory_candidates(n_cand, seed=7):
 def run_factory(ctx, rank, world, cands_per_gpu, barrier):
     """fgpm_factory candidate scoring (second headline metric): n = 1024, candidates sharded over the ranks."""
     from fungp_b200 import synth, factory as F
-    from fungp_b200.shard import shard_range
     from fungp_b200.model import NumpyRng
     sIn, fIn, y = synth.make_data(FACTORY["seed"], FACTORY["n"], FACTORY["ds"], FACTORY["f_lens"])
     ants = factory_candidates(cands_per_gpu * world)
-    b0, b1 = shard_range(len(ants), rank, world)
-    F.score_candidates(ctx, sIn, fIn, y, ants[b0:b0 + 2], NumpyRng(0), nugget=FACTORY["nugget"])       # warm-up
+    mine = ants[rank::world]            # round-robin deal: candidate costs vary with the structure, this evens them out
+    F.score_candidates(ctx, sIn, fIn, y, mine[:2], NumpyRng(0), nugget=FACTORY["nugget"])       # warm-up
     barrier()
     t0 = time.perf_counter()
-    res = F.score_candidates(ctx, sIn, fIn, y, ants[b0:b1], NumpyRng(rank + 1), nugget=FACTORY["nugget"],
+    res = F.score_candidates(ctx, sIn, fIn, y, mine, NumpyRng(rank + 1), nugget=FACTORY["nugget"],
                              n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"])
     barrier()
     return time.perf_counter() - t0, len(ants), int((res["info"] == 0).sum()), float(np.nanmax(res["fitness"]))
