@@ -100,7 +100,7 @@ struct fgp_ctx {
     int profile = 0;
     int lookahead = 1;
     int streams = 8;
-    int fit_workers = 6;      // fgp_fit_batch: concurrent candidate fits per GPU
+    int fit_workers = 8;      // fgp_fit_batch: concurrent candidate fits per GPU
     int outer = 16;           // column tiles per outer panel for batches (trailing update K = outer*128)
     int outer_single = 2;     // same for a single factorisation with look-ahead (its panel chain is exposed)
     double timing[8] = {0};

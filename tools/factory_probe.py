@@ -11,7 +11,7 @@ ctx = fungp_b200.Context(1)
 sIn, fIn, y = synth.make_data(1024, 1024, 5, [10, 22, 50])
 ants = bench.factory_candidates(96)
 base = None
-for w in (1, 4, 4, 8, 8):
+for w in (1, 4, 8, 8, 12, 16):
     ctx.set_option("fit_workers", w)
     t0 = time.perf_counter()
     r = F.score_candidates(ctx, sIn, fIn, y, ants, NumpyRng(1))
