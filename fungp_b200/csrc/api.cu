@@ -385,11 +385,14 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
     const size_t matBytes = sizeof(double) * (size_t)ld * n;
     const int ncT = cdiv(n, FGP_TILE);
     const size_t wBytes = sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE;
-    size_t freeB = 0, totB = 0;
-    cudaMemGetInfo(&freeB, &totB);
-    size_t budget = std::min<size_t>((size_t)((freeB + d.work.cap + d.wbuf.cap) * 0.6), (size_t)32 << 30);
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, budget / (matBytes + wBytes)));
-    chunk = std::min(chunk, 4096);
+    int chunk = std::min(B, 4096);
+    if (matBytes * chunk > d.work.cap || wBytes * chunk > d.wbuf.cap) {
+        // the workspaces must grow: size the chunk against what the device has left (not on the steady-state path)
+        size_t freeB = 0, totB = 0;
+        cudaMemGetInfo(&freeB, &totB);
+        const size_t budget = std::min<size_t>((size_t)((freeB + d.work.cap + d.wbuf.cap) * 0.6), (size_t)32 << 30);
+        chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)chunk, budget / (matBytes + wBytes)));
+    }
     if (d.work.ensure(matBytes * chunk) || d.wbuf.ensure(wBytes * chunk)) {
         fgp_set_err(ctx, "fgp_nll_batch: out of device memory");
         return FGP_ERR_ALLOC;

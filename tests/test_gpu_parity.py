@@ -32,7 +32,7 @@ def _problem(ctx, case):
 
 
 def _rel(a, b, floor):
-    return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), floor))
+    return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), max(floor, 1e-300)))
 
 
 def _nll_tol(nll_ref, n, floor=0.0):
@@ -104,6 +104,9 @@ def test_stored_models(ctx, name):
 
 CASES = [
     # (seed, n, ds, f_lens, pdims, bas, dis, ker, frac)
+    (7, 1, 2, [], [], [], [], "matern5_2", 0.5),
+    (8, 2, 1, [6], [2], ["B-splines"], ["L2_bygroup"], "gauss", 0.5),
+    (9, 5, 2, [8], [0], ["B-splines"], ["L2_byindex"], "matern3_2", 0.5),
     (11, 25, 2, [10, 22], [3, 3], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
     (12, 127, 1, [], [], [], [], "gauss", 0.1),
     (13, 128, 0, [12], [4], ["B-splines"], ["L2_byindex"], "matern3_2", 0.5),
@@ -124,6 +127,7 @@ def test_assemble_and_nll(ctx, spec):
     Ms = oracle_dists(case)
     P = _problem(ctx, case)
     theta = theta_frac(Ms, frac)
+    theta = np.where(theta > 0, theta, 1.0)        # n = 1: every distance is 0, any positive length-scale will do
     nug = 1e-8
     np.testing.assert_allclose(P.dist_max(), [M.max() for M in Ms], rtol=1e-12)
     if n <= 1100:
