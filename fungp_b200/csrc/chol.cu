@@ -157,7 +157,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
             g.A = t.M + (long)k0 * t.ld;
             g.B = t.W + (long)kk * NBk * NBk; g.ldb = NBk; g.strideB = t.strideW;
             g.C = t.M + (long)k0 * t.ld;
-            g.K = nb; g.accumulate = 0;
+            g.K = nb; g.accumulate = 0; g.bLowerTri = 1;
             g.tri0 = 0; g.triT = 0;
             int tlo1 = S.lo1, thi1 = S.hi1;
             if (fresh && nb < NBk && (long)k0 + nb < (long)std::min(t.nrows, (kk + 1) * NBk)) {

@@ -108,6 +108,7 @@ struct GemmArgs {
     int rowMin, rowLo, rowHoleHi, nrows;       // valid r: r >= rowMin && (r < rowLo || (rowHoleHi <= r < nrows))
     int colMin, colLo, colHoleHi, ncols;       // same for c
     int batch;
+    int bLowerTri;                             // 1: B(c, k) = 0 for k > c (panel solve with inv(L_kk)): skip the zero half
     int maxTilesPerCta;                        // 0 = automatic; 1 = one tile per CTA (look-ahead: the panel stream must find a free SM quickly)
     int dbg;                                   // experiment switches, honoured only when built with -DFGP_GEMM_DEBUG
 };

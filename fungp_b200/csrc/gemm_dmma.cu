@@ -155,8 +155,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g, 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int wm = warp & 3;   // 4 warps along m (32 rows each)
-    const int wn = warp >> 2;  // 2 warps along n (64 cols each)
+    // warps (wm, wn): 4 along m (32 rows each) x 2 along n (64 cols each).  Scheduler = warp % 4: the two warps of one
+    // scheduler get different wn (the panel solve's triangular B halves the work of wn = 0: both schedulers stay
+    // balanced) and the two warps with the same wm sit on different schedulers (a tile with few valid rows, e.g. the
+    // one-row y tile, still spreads over two of them)
+    const int wn = (warp >> 2) & 1;
+    const int wm = (warp + wn) & 3;
     const long b = blockIdx.y;
     const double* A = g.A + b * g.strideA;
     const double* B = g.B + b * g.strideB;
@@ -231,6 +235,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g, 
         if (g.accumulate && tl.inTri && tl.I == tl.J && (wm * 32 + 31 < wn * 64)) active = false;
         if (!active) rmask = 0;
         const bool full = __all_sync(0xffffffffu, rmask == 0xFu && cmask == 0xFFFFu);
+        // 8-row blocks of this warp that hold at least one valid row (warp-uniform): the others are not multiplied
+        unsigned mval = 0;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+            if (__any_sync(0xffffffffu, (rmask >> mi) & 1u)) mval |= 1u << mi;
         double* Cw = C + (long)(wrow + r_lane) + (long)(wcol + c_lane) * g.ldc;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -291,7 +300,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g, 
             const bool kokA = (cn * KC + qa.kq) < g.K, kokB = (cn * KC + qb.kq) < g.K;
             const double* srcA = qa.gptr + (long)(cn * KC) * g.lda;
             const double* srcB = qb.gptr + (long)(cn * KC) * g.ldb;
-            if (active && !DBG(16)) {
+            // panel solve: B = inv(L_kk) is lower triangular, B(c, k) = 0 for k > c -> columns < 64 need k < 64 only
+            const bool skipChunk = g.bLowerTri && (c * KC >= (wn + 1) * 64);
+            if (active && !skipChunk && !DBG(16)) {
                 const double* As = smem + (gc % STAGES) * STAGE + (wm * 4) * (KC / 4) * 32 + fragoff;
                 const double* Bs = smem + (gc % STAGES) * STAGE + OPER + (wn * 8) * (KC / 4) * 32 + fragoff;
 #pragma unroll
@@ -313,10 +324,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g, 
                         issue_piece(qa, stA, srcA, kokA, 2 * (kk - KC / 8) + 1);
                         issue_piece(qb, stB, srcB, kokB, 2 * (kk - KC / 8) + 1);
                     }
+                    if (mval == 0xFu) {
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
+                        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                            for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                    } else {
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            if ((mval >> mi) & 1u) {
+#pragma unroll
+                                for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                            }
+                    }
                 }
             } else if (doCopy) {
                 if ((gc + STAGES - 1) >= STAGES)
