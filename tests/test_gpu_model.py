@@ -62,9 +62,11 @@ def test_fit_predict_simulate_update_vs_oracle(ctx, ker, n_starts):
               nugget=1e-8, n_starts=n_starts, n_presample=20)
     g = M.fgpm(sIn=sIn[tr], fIn=[f[tr] for f in fIn], sOut=y[tr], rng=RRng(5), ctx=ctx, **kw)
     o = ref.fgpm(sIn=sIn[tr], fIn=[f[tr] for f in fIn], sOut=y[tr], rng=RRng(5), **kw)
-    # same optimiser, same starts, nll identical to ~1e-12 => same trajectory up to FP noise
+    # same optimiser, same starts, nll identical to ~1e-12 => same trajectory up to FP noise.  L-BFGS-B stops on a
+    # relative decrease of factr * eps = 2.2e-9, so the end point along a flat direction of the likelihood is only
+    # determined to ~1e-4 relative while the optimum value itself agrees to 1e-8
     assert abs(g.negLogLik - o.negLogLik) <= 1e-8 * max(abs(o.negLogLik), n)
-    np.testing.assert_allclose(np.r_[g.kern.s_lsHyps, g.kern.f_lsHyps], o.lsHyps, rtol=2e-5)
+    np.testing.assert_allclose(np.r_[g.kern.s_lsHyps, g.kern.f_lsHyps], o.lsHyps, rtol=1e-4)
     assert abs(g.kern.varHyp - o.varHyp) <= 1e-4 * o.varHyp
     # predict / simulate with the ORACLE evaluated at the GPU model's hyper-parameters (isolates the algebra)
     o2 = ref.fgpm(sIn=sIn[tr], fIn=[f[tr] for f in fIn], sOut=y[tr], kerType=ker, f_disType=kw["f_disType"],

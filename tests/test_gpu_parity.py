@@ -256,3 +256,36 @@ def test_large_n_properties(ctx):
     assert abs(nll[0] - r_nll) <= _nll_tol(r_nll, n)
     assert abs(sig2[0] - r_s2) <= 1e-7 * r_s2
     P.close()
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_device_projection_stored_models(ctx, name):
+    """dimReduction with the contractions on the device (fgp_project with a context) against the basis / coefs
+    stored in the reference's own fitted models (R/7_dimRedFunctions.R:7-60)."""
+    g = load_models()[name]
+    if not g["df"]:
+        pytest.skip("scalar-only model")
+    for f, p, bt, Bg, cg in zip(g["fIn"], g["f_pdims"], g["f_basType"], g["basis"], g["coefs"]):
+        Bo, J, co = ctx.project(np.asarray(f), p, bt)
+        sg = np.sign(np.sum(Bo * Bg, axis=0)) if bt == "PCA" else 1.0      # quirk Q7: PCA sign is LAPACK's
+        np.testing.assert_allclose(Bo * sg, Bg, atol=1e-12)
+        np.testing.assert_allclose(co * sg, cg, atol=1e-11)
+        _, _, co2 = ctx.project(np.asarray(f), p, bt, B=Bg)               # re-projection (predict / simulate)
+        np.testing.assert_allclose(co2, cg, atol=1e-11)
+
+
+@pytest.mark.parametrize("n,k,p,bt", [(1, 12, 3, "B-splines"), (7, 9, 9, "B-splines"), (300, 37, 11, "B-splines"),
+                                      (2, 5, 1, "PCA"), (250, 18, 6, "PCA"), (4096, 100, 5, "PCA"),
+                                      (32768, 200, 10, "B-splines"), (50, 8, 0, "B-splines")])
+def test_device_projection_vs_oracle(ctx, n, k, p, bt):
+    rng = np.random.default_rng(n + k)
+    f = np.cumsum(rng.standard_normal((n, k)), axis=1) / np.sqrt(k) + rng.random((n, 1))
+    Bo, J, co = ctx.project(f, p, bt)
+    r = ref.dimReduction([f], [p], [bt])
+    Br, cr = r["basis"][0], r["coefs"][0]
+    sg = np.sign(np.sum(Bo * Br, axis=0)) if bt == "PCA" and p else 1.0
+    scale = max(1.0, np.abs(cr).max())
+    np.testing.assert_allclose(Bo * sg, Br, atol=1e-10 if bt == "PCA" else 1e-13)
+    np.testing.assert_allclose(co * sg, cr, rtol=0, atol=(1e-9 if bt == "PCA" else 1e-11) * scale)
+    np.testing.assert_allclose(J, r["J"][0], atol=1e-12)
+    _log("device_projection", n=n, k=k, p=p, basis=bt, coef_abs_err=float(np.abs(co * sg - cr).max()))
