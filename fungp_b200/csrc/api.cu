@@ -163,6 +163,62 @@ extern "C" int fgp_measure_peaks(fgp_ctx* ctx, double* dmma_tflops, double* dfma
 }
 
 // ------------------------------------------------------------------------------------------------ problem
+// lower factor W (p x p, column-major) with J = W W': Cholesky; if J is not numerically positive definite (rank-
+// deficient basis), the symmetric eigen-decomposition with negative eigenvalues clamped (the reference clamps the
+// resulting squared distances at 0 instead, R/7_distanceFunctions.R:44)
+void whitening_factor(const double* J, int p, std::vector<double>& W) {
+    W.assign((size_t)p * p, 0.0);
+    bool ok = true;
+    for (int j = 0; j < p && ok; ++j) {
+        double d = J[j + (size_t)j * p];
+        for (int q = 0; q < j; ++q) d -= W[j + (size_t)q * p] * W[j + (size_t)q * p];
+        if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
+        const double l = sqrt(d);
+        W[j + (size_t)j * p] = l;
+        for (int i = j + 1; i < p; ++i) {
+            double v = 0.5 * (J[i + (size_t)j * p] + J[j + (size_t)i * p]);
+            for (int q = 0; q < j; ++q) v -= W[i + (size_t)q * p] * W[j + (size_t)q * p];
+            W[i + (size_t)j * p] = v / l;
+        }
+    }
+    if (ok) return;
+    // cyclic Jacobi on the symmetrised J
+    std::vector<double> A((size_t)p * p), V((size_t)p * p, 0.0);
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < p; ++j) A[i + (size_t)j * p] = 0.5 * (J[i + (size_t)j * p] + J[j + (size_t)i * p]);
+    for (int i = 0; i < p; ++i) V[i + (size_t)i * p] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int j = 0; j < p; ++j)
+            for (int i = 0; i < p; ++i) (i == j ? dg : off) += A[i + (size_t)j * p] * A[i + (size_t)j * p];
+        if (off <= 1e-32 * dg || off == 0.0) break;
+        for (int a = 0; a < p - 1; ++a)
+            for (int b = a + 1; b < p; ++b) {
+                const double apq = A[a + (size_t)b * p];
+                if (apq == 0.0) continue;
+                const double th = (A[b + (size_t)b * p] - A[a + (size_t)a * p]) / (2.0 * apq);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int r = 0; r < p; ++r) {
+                    const double x = A[r + (size_t)a * p], y = A[r + (size_t)b * p];
+                    A[r + (size_t)a * p] = c * x - sn * y; A[r + (size_t)b * p] = sn * x + c * y;
+                }
+                for (int r = 0; r < p; ++r) {
+                    const double x = A[a + (size_t)r * p], y = A[b + (size_t)r * p];
+                    A[a + (size_t)r * p] = c * x - sn * y; A[b + (size_t)r * p] = sn * x + c * y;
+                }
+                for (int r = 0; r < p; ++r) {
+                    const double x = V[r + (size_t)a * p], y = V[r + (size_t)b * p];
+                    V[r + (size_t)a * p] = c * x - sn * y; V[r + (size_t)b * p] = sn * x + c * y;
+                }
+            }
+    }
+    for (int j = 0; j < p; ++j) {
+        const double w = sqrt(std::max(0.0, A[j + (size_t)j * p]));
+        for (int i = 0; i < p; ++i) W[i + (size_t)j * p] = V[i + (size_t)j * p] * w;
+    }
+}
+
 void build_coords(const fgp_problem* P, int m, const double* sIn, const double* const* coefs, std::vector<double>& X) {
     X.assign((size_t)m * P->ncoord, 0.0);
     int col = 0;
@@ -173,16 +229,16 @@ void build_coords(const fgp_problem* P, int m, const double* sIn, const double* 
         if (P->dis[i] == FGP_DIST_BYINDEX) {
             for (int a = 0; a < p; ++a, ++col) memcpy(&X[(size_t)col * m], c + (size_t)a * m, sizeof(double) * m);
         } else {
-            if (col & 1) ++col;   // group units start on an even column (they are staged as pairs)
-            const double* J = P->J[i].data();
-            for (int a = 0; a < p; ++a, col += 2) {
-                memcpy(&X[(size_t)col * m], c + (size_t)a * m, sizeof(double) * m);
-                double* e = &X[(size_t)(col + 1) * m];
-                // (f J)[, a] = sum_b f[, b] J[b, a]      (R/7_distanceFunctions.R:39-40)
+            // whitened coefficients z = c W, J = W W': ||z_i - z_j||^2 = (c_i - c_j)' J (c_i - c_j)
+            // (the bilinear form of R/7_distanceFunctions.R:39-45)
+            const double* W = P->Jw[i].data();
+            for (int a = 0; a < p; ++a, ++col) {
+                double* z = &X[(size_t)col * m];
                 for (int b = 0; b < p; ++b) {
-                    const double jba = J[b + (size_t)a * p];
+                    const double wba = W[b + (size_t)a * p];
+                    if (wba == 0.0) continue;
                     const double* cb = c + (size_t)b * m;
-                    for (int r = 0; r < m; ++r) e[r] += cb[r] * jba;
+                    for (int r = 0; r < m; ++r) z[r] += cb[r] * wba;
                 }
             }
         }
@@ -234,15 +290,16 @@ extern "C" int fgp_problem_create(fgp_ctx* ctx, int n, int ds, const double* sIn
         }
         P->p.push_back(p[i]); P->dis.push_back(dis_type[i]);
         P->J.emplace_back(J[i], J[i] + (size_t)p[i] * p[i]);
+        P->Jw.emplace_back();
+        if (dis_type[i] == FGP_DIST_BYGROUP) whitening_factor(J[i], p[i], P->Jw.back());
         if (dis_type[i] == FGP_DIST_BYINDEX) {
             for (int a = 0; a < p[i]; ++a) {
                 P->termFirstUnit.push_back((int)P->units.size());
                 P->units.push_back({0, col++, term++, 1});
             }
         } else {
-            if (col & 1) ++col;
             P->termFirstUnit.push_back((int)P->units.size());
-            for (int a = 0; a < p[i]; ++a, col += 2) P->units.push_back({1, col, term, a == p[i] - 1});
+            for (int a = 0; a < p[i]; ++a) P->units.push_back({1, col++, term, a == p[i] - 1});
             ++term;
         }
     }

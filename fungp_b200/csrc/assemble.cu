@@ -8,20 +8,23 @@
 //   matern5_2  prod_l (1 + a_l + a_l^2/3) * exp(-sum_l a_l),  a_l = sqrt5 d_l / theta_l
 //   matern3_2  prod_l (1 + a_l)           * exp(-sum_l a_l),  a_l = sqrt3 d_l / theta_l
 // Differences are formed first and scaled afterwards (x_i - x_j is exact for close points; scaling the
-// coordinates first would lose that), and L2_bygroup keeps the reference's bilinear form
-// sum_a (c_ia - c_ja)(e_ia - e_ja), e = c J, clamped at 0 before the square root (R/7_distanceFunctions.R:42-45).
+// coordinates first would lose that).  L2_bygroup terms arrive whitened (z = c chol(J), api.cu build_coords), so
+// that the reference's bilinear form (c_i - c_j)' J (c_i - c_j) (R/7_distanceFunctions.R:42-45) is a plain sum of
+// squares -- one coordinate column, one subtraction and one fused multiply-add per coefficient and entry.
 //
 // Tiling: 64 x 64 output tile per CTA, 256 threads, 4 x 4 entries per thread arranged so that every store
 // instruction writes 256 contiguous bytes per half-warp of the column-major destination; only tiles on or
-// below the diagonal are produced for symmetric blocks; coordinates are staged through shared memory in
-// chunks of 16 columns.  The kernel is bound by FP64 issue (about 3 DFMA-class ops per unit and entry plus one
-// exp), not by HBM -- see DESIGN.md for the op count against the 8 bytes written per entry.
+// below the diagonal are produced for symmetric blocks; up to 32 coordinate columns of both point sets and the
+// metadata of their units are staged through shared memory per pass (one pass for every BASELINE configuration),
+// read back with 16-byte loads.  The kernel is bound by FP64 issue, not by HBM: about 2-3 FP64 instructions per
+// coordinate and entry plus an 18-instruction exp against 8 bytes written, on a machine whose DFMA and DMMA share
+// one FP64 datapath (profiles/r01_peaks.md) -- see DESIGN.md 2.3 for the count.
 #include "common.cuh"
 
 namespace {
 
 constexpr int AT = 64;       // tile edge
-constexpr int CC = 16;       // coordinate columns staged per chunk
+constexpr int CC = 32;       // coordinate columns staged per pass
 constexpr int ATHREADS = 256;
 
 enum { MODE_STORE = 0, MODE_MAX = 1 };
@@ -40,11 +43,41 @@ __device__ __forceinline__ void tri_decode(int t, int& I, int& J) {
     J = t - i * (i + 1) / 2;
 }
 
+// exp(t) for t <= 0 without the special-case branches of the library routine: t = k ln2 + r, |r| <= ln2/2, a degree-12
+// Taylor polynomial (truncation 0.3466^13/13! = 1.7e-16) and the exponent added to the high word.  Below -708 the
+// result is flushed to 0 (the true value is < 3.4e-308).
+__device__ __forceinline__ double exp_nonpos(double t) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: rounds to nearest integer in the low word
+    const double kd = fma(t, 1.4426950408889634, MAGIC);
+    const int k = __double2loint(kd);
+    const double kf = kd - MAGIC;
+    double r = fma(kf, -6.93147180369123816490e-01, t);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;                 // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);             // 1/11!
+    p = fma(p, r, 2.75573192239858906526e-07);             // 1/10!
+    p = fma(p, r, 2.75573192239858906526e-06);             // 1/9!
+    p = fma(p, r, 2.48015873015873015873e-05);             // 1/8!
+    p = fma(p, r, 1.98412698412698412698e-04);             // 1/7!
+    p = fma(p, r, 1.38888888888888888889e-03);             // 1/6!
+    p = fma(p, r, 8.33333333333333333333e-03);             // 1/5!
+    p = fma(p, r, 4.16666666666666666667e-02);             // 1/4!
+    p = fma(p, r, 1.66666666666666666667e-01);             // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return t < -708.0 ? 0.0 : res;
+}
+
 // KER: 0 = raw distance of the (single) term, 1 gauss, 2 matern5_2, 3 matern3_2
 template <int KER, int MODE>
-__global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
-    __shared__ double sP[CC][AT];
-    __shared__ double sQ[CC][AT];
+__global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
+    __shared__ __align__(16) double sP[CC][AT];
+    __shared__ __align__(16) double sQ[CC][AT];
+    __shared__ double sScale[CC];
+    __shared__ int sCol[CC];
+    __shared__ int sFlag[CC];       // bit 0: member of a group term, bit 1: last unit of its term
     __shared__ double sRed[ATHREADS / 32];
     const AsmArgs& a = k.a;
     const int tid = threadIdx.x;
@@ -60,7 +93,7 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
     const double* scale = a.scale ? a.scale + (long)blockIdx.y * a.nterms : nullptr;
 
     // this thread's rows (local): 2tx, 2tx+1, 32+2tx, 33+2tx ; cols: 4ty .. 4ty+3
-    int lr[4] = {2 * tx, 2 * tx + 1, 32 + 2 * tx, 33 + 2 * tx};
+    const int lr[4] = {2 * tx, 2 * tx + 1, 32 + 2 * tx, 33 + 2 * tx};
     const int lc0 = 4 * ty;
 
     double S[4][4], Pr[4][4], D2[4][4];
@@ -69,35 +102,36 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { S[i][j] = 0.0; Pr[i][j] = 1.0; D2[i][j] = 0.0; }
 
-    int u = k.u0;
-    const int colBegin = (k.u0 < k.u1) ? (a.units[k.u0].col / CC) * CC : 0;
-    const int colEnd = (k.u0 < k.u1) ? a.units[k.u1 - 1].col + (a.units[k.u1 - 1].kind ? 2 : 1) : 0;
-    for (int cbase = colBegin; cbase < colEnd; cbase += CC) {
+    for (int ub = k.u0; ub < k.u1; ub += CC) {
+        const int nc = min(CC, k.u1 - ub);
         __syncthreads();
-        // stage CC columns x 64 points of each side (coalesced along points)
-        for (int idx = tid; idx < CC * AT; idx += ATHREADS) {
-            const int c = idx / AT, pnt = idx % AT;
-            const int col = cbase + c;
-            double vp = 0.0, vq = 0.0;
-            if (col < colEnd) {
-                if (i0 + pnt < a.nP) vp = a.XP[(long)col * a.ldP + i0 + pnt];
-                if (j0 + pnt < a.nQ) vq = a.XQ[(long)col * a.ldQ + j0 + pnt];
-            }
-            sP[c][pnt] = vp;
-            sQ[c][pnt] = vq;
+        if (tid < nc) {
+            const FgpUnit un = a.units[ub + tid];
+            sCol[tid] = un.col;
+            sFlag[tid] = (un.kind ? 1 : 0) | (un.last ? 2 : 0);
+            sScale[tid] = (KER == 0) ? 1.0 : scale[un.term];
         }
         __syncthreads();
-        while (u < k.u1) {
-            const FgpUnit un = a.units[u];
-            if (un.col >= cbase + CC) break;
-            const int c = un.col - cbase;
-            double xp[4], xq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xp[i] = sP[c][lr[i]];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) xq[j] = sQ[c][lc0 + j];
-            if (un.kind == 0) {
-                const double sc = (KER == 0) ? 1.0 : scale[un.term];
+        // stage nc columns x 64 points of each side (coalesced along points)
+        for (int idx = tid; idx < nc * AT; idx += ATHREADS) {
+            const int c = idx / AT, pnt = idx % AT;
+            const long col = sCol[c];
+            sP[c][pnt] = (i0 + pnt < a.nP) ? a.XP[col * a.ldP + i0 + pnt] : 0.0;
+            sQ[c][pnt] = (j0 + pnt < a.nQ) ? a.XQ[col * a.ldQ + j0 + pnt] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c = 0; c < nc; ++c) {
+            const double2 p01 = *reinterpret_cast<const double2*>(&sP[c][2 * tx]);
+            const double2 p23 = *reinterpret_cast<const double2*>(&sP[c][32 + 2 * tx]);
+            const double2 q01 = *reinterpret_cast<const double2*>(&sQ[c][lc0]);
+            const double2 q23 = *reinterpret_cast<const double2*>(&sQ[c][lc0 + 2]);
+            const double xp[4] = {p01.x, p01.y, p23.x, p23.y};
+            const double xq[4] = {q01.x, q01.y, q23.x, q23.y};
+            const int flag = sFlag[c];
+            const double sc = sScale[c];
+            if (!(flag & 1)) {
+                // index unit: scalar input or one L2_byindex coefficient, its own length-scale
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -115,25 +149,24 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
                         }
                     }
             } else {
-                double ep[4], eq[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ep[i] = sP[c + 1][lr[i]];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) eq[j] = sQ[c + 1][lc0 + j];
+                // member of an L2_bygroup term (whitened coefficients): squared differences add up
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) D2[i][j] = fma(xp[i] - xq[j], ep[i] - eq[j], D2[i][j]);
-                if (un.last) {
-                    const double sc = (KER == 0) ? 1.0 : scale[un.term];
+                    for (int j = 0; j < 4; ++j) {
+                        const double d = xp[i] - xq[j];
+                        D2[i][j] = fma(d, d, D2[i][j]);
+                    }
+                if (flag & 2) {
+                    const double sc2 = sc * sc;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const double d2 = fmax(D2[i][j], 0.0);
+                            const double d2 = D2[i][j];
                             D2[i][j] = 0.0;
                             if (KER == 0) S[i][j] = sqrt(d2);
-                            else if (KER == 1) S[i][j] = fma(d2, sc * sc, S[i][j]);
+                            else if (KER == 1) S[i][j] = fma(d2, sc2, S[i][j]);
                             else {
                                 const double av = sqrt(d2) * sc;
                                 S[i][j] += av;
@@ -143,7 +176,6 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
                         }
                 }
             }
-            ++u;
         }
     }
 
@@ -167,6 +199,8 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
 
     // ---- finish + store
     double* M = a.M + (long)blockIdx.y * a.strideM;
+    const bool scaled = a.mult != 1.0;
+    const bool diagTile = a.sym && I == J;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int gj = j0 + lc0 + j;
@@ -174,13 +208,14 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(AsmK k) {
         double v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int gi = i0 + lr[i];
             double r;
             if (KER == 0) r = S[i][j];
-            else if (KER == 1) r = exp(-0.5 * S[i][j]);
-            else r = Pr[i][j] * exp(-S[i][j]);
-            const bool dg = a.sym && (gi == gj);
-            if (KER != 0) r = a.mult * (r + (dg ? a.diag_rel : 0.0)) + (dg ? a.diag_abs : 0.0);
+            else if (KER == 1) r = exp_nonpos(-0.5 * S[i][j]);
+            else r = Pr[i][j] * exp_nonpos(-S[i][j]);
+            if (KER != 0) {
+                if (diagTile && lr[i] == lc0 + j) r = a.mult * (r + a.diag_rel) + a.diag_abs;
+                else if (scaled) r *= a.mult;
+            }
             v[i] = r;
         }
         double* colp = M + (long)(a.colOff + gj) * a.ld + a.rowOff;

@@ -37,7 +37,7 @@ void fgp_set_err_cuda(fgp_ctx* ctx, const char* what, cudaError_t e, const char*
 // ---------------------------------------------------------------------------------------------------------
 // coordinate "units" consumed by the assembly kernels (one per squared-difference term)
 //   kind 0: index unit  -- one column x;            d = |x_i - x_j|            (L2_byindex, scalar inputs)
-//   kind 1: group unit  -- two columns (c_a, e_a);  d^2 += (c_ia-c_ja)(e_ia-e_ja), e = c J  (L2_bygroup)
+//   kind 1: group unit  -- one column z_a of the whitened coefficients z = c W, J = W W';  d^2 += (z_ia-z_ja)^2  (L2_bygroup)
 // `last` marks the unit that closes its length-scale term.
 struct FgpUnit {
     int kind;

@@ -128,7 +128,8 @@ struct fgp_problem {
     std::vector<int> termFirstUnit;     // nterms + 1
     std::vector<double> X;    // host copy (replicated lazily to the other devices)
     std::vector<double> y;
-    std::vector<std::vector<double>> J;   // per functional input (p x p), needed to build e = c J for new points
+    std::vector<std::vector<double>> J;   // per functional input (p x p), as given
+    std::vector<std::vector<double>> Jw;  // per functional input: W with J = W W' (L2_bygroup; empty otherwise), whitens new points too
     std::vector<ProblemDev> pd;
     // model state
     bool hasModel = false;

@@ -289,3 +289,25 @@ def test_device_projection_vs_oracle(ctx, n, k, p, bt):
     np.testing.assert_allclose(co * sg, cr, rtol=0, atol=(1e-9 if bt == "PCA" else 1e-11) * scale)
     np.testing.assert_allclose(J, r["J"][0], atol=1e-12)
     _log("device_projection", n=n, k=k, p=p, basis=bt, coef_abs_err=float(np.abs(co * sg - cr).max()))
+
+
+def test_assembly_exp_accuracy(ctx):
+    """The assembly kernel's branch-free exp (csrc/assemble.cu exp_nonpos) over its whole range: one scalar input on a
+    line, gauss kernel, so that the entries are exp(-d^2 / 2 theta^2) for arguments from 0 down to the flush at -708."""
+    import fungp_b200
+    n = 2048
+    rng = np.random.default_rng(11)
+    x = np.sort(rng.random(n)) * 40.0
+    P = fungp_b200.Problem(ctx, x[:, None], [], [], [], np.zeros(n))
+    R = P.assemble("gauss", 0.0, np.array([1.0]))
+    d = np.abs(x[:, None] - x[None, :])
+    t = -0.5 * d * d
+    want = np.exp(t)
+    low = np.tril_indices(n)
+    got, want, t = R[low], want[low], t[low]
+    big = t > -700.0
+    rel = np.abs(got[big] - want[big]) / want[big]
+    _log("assembly_exp", max_rel=float(rel.max()), n_args=int(big.sum()))
+    assert rel.max() <= 4.5e-16     # <= 2 ulp against numpy exp
+    assert np.all(got[~big] <= 1e-300) and np.all(got >= 0.0)
+    P.close()
