@@ -290,7 +290,7 @@ def run_ours(args):
             "roofline_assembly": {"bound": "hbm", "kernel": "assemble_kernel<gauss> (fused distance + correlation, lower triangle)",
                                   "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                                   "algorithmic_bytes_per_launch": asm_bytes / 2, "launch_ms": tm["assembly_ms"] / 2,
-                                  "note": "FP64-issue co-bound: ~45 DFMA-class ops + one exp per 8-byte entry at d=6 (DESIGN.md)"},
+                                  "note": "FP64-issue bound: 53.5 FP64 instructions per 8-byte entry at this structure (ncu), DMMA and DFMA share one datapath; kernel ceiling = 41 % of HBM (DESIGN.md 2.3)"},
             "kernel_ms_profiled_2evals": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
             "fp64_peaks_measured": peaks,
             "nll_check": float(nll_last[0]),
