@@ -311,3 +311,51 @@ def test_assembly_exp_accuracy(ctx):
     assert rel.max() <= 4.5e-16     # <= 2 ulp against numpy exp
     assert np.all(got[~big] <= 1e-300) and np.all(got >= 0.0)
     P.close()
+
+
+def test_c5_size_properties(ctx):
+    """n = 32768 (BASELINE configs[4]: 2 scalar + 2 functional of length 200, k = 10, matern3_2; one 8.6 GB covariance).
+    The oracle cannot run here in test time, so the checks are size-independent properties of the path:
+    batched vs look-ahead factorisation agree; nll(2y) - nll(y) = n log 2 and sig2 scales by 4 (concentrated
+    likelihood, R/3_training_SF.R:215-220); the predictive mean is linear in y and the sd does not depend on y
+    (R/4_prediction_SF.R:9-17); prediction at training points interpolates."""
+    n, m = 32768, 256
+    case = make_case(5, n, 2, [200, 200], [10, 10], ["B-splines"] * 2, ["L2_bygroup"] * 2, extra=m)
+    P = _problem(ctx, case)
+    y = case["y"]
+    theta = 0.3 * 2.0 * P.dist_max()
+    ker, nug = "matern3_2", 1e-8
+    nll1, s1, info1 = P.nll_batch(ker, nug, theta)
+    nll2, s2, info2 = P.nll_batch(ker, nug, np.stack([theta, theta], axis=1))
+    assert info1[0] == 0 and (info2 == 0).all() and nll2[0] == nll2[1]
+    scale = max(abs(nll1[0]), n)
+    assert abs(nll1[0] - nll2[0]) <= 1e-9 * scale and abs(s1[0] - s2[0]) <= 1e-9 * s1[0]
+    P.set_y(2.0 * y)
+    nll3, s3, _ = P.nll_batch(ker, nug, theta)
+    assert abs((nll3[0] - nll1[0]) - n * np.log(2.0)) <= 1e-9 * scale
+    assert abs(s3[0] - 4.0 * s1[0]) <= 1e-12 * s3[0]
+    # linearity of the predictor at m new points, fixed hyper-parameters and variance
+    rng = np.random.default_rng(0)
+    ya = y
+    yb = rng.standard_normal(n)
+    means, sds = [], []
+    for yy in (ya, yb, ya + yb):
+        P.set_y(yy)
+        P.premats(ker, nug, s1[0], theta, want_L=False)
+        pr = P.predict(m, case["sNew"], case["coefsNew"])
+        means.append(pr["mean"]); sds.append(pr["sd"])
+    sd0 = np.sqrt(s1[0])
+    lin = np.max(np.abs(means[2] - means[0] - means[1]))
+    assert lin <= 1e-8 * max(1.0, np.max(np.abs(means[2])))
+    assert np.max(np.abs(sds[0] - sds[1])) == 0.0 and np.all(sds[0] >= 0) and np.all(sds[0] <= sd0 * (1 + 1e-6))
+    # interpolation at 256 training points (nugget 1e-8): back to y, sd far below the prior sd
+    idx = rng.choice(n, 256, replace=False)
+    P.set_y(ya)
+    P.premats(ker, nug, s1[0], theta, want_L=False)
+    pr = P.predict(256, case["sIn"][idx], [c[idx] for c in case["coefs"]])
+    mu_t, sd_t = pr["mean"], pr["sd"]
+    _log("c5_size", n=n, nll=float(nll1[0]), path_diff=float(abs(nll1[0] - nll2[0])), linearity=float(lin),
+         interp_err=float(np.max(np.abs(mu_t - ya[idx]))), interp_sd_over_prior=float(np.max(sd_t) / sd0))
+    assert np.max(np.abs(mu_t - ya[idx])) <= 1e-3 * (np.max(ya) - np.min(ya))
+    assert np.max(sd_t) <= 1e-2 * sd0
+    P.close()
