@@ -28,7 +28,7 @@ constexpr int SB = 32;
 constexpr int XLD = 132;     // XP[k][row]
 constexpr int ELD = 36;      // Eop[k][n]
 constexpr int POTF2_THREADS = 256;
-constexpr int POTF2_SMEM = (NB * LDT + SB * XLD + SB * ELD + SB + NB) * 8;
+constexpr int POTF2_SMEM = (NB * LDT + SB * XLD + SB * ELD + SB + NB + SB + SB) * 8;
 
 // 1/sqrt(d) for the pivots: MUFU seed (rsqrt.approx, ~2^-20 relative) + one cubically convergent correction, all
 // FMA: 49 cycles of latency against 94 for the libdevice rsqrt() and 160 for sqrt() (tools/lat_bench.cu).
@@ -39,11 +39,45 @@ __device__ __forceinline__ double pivot_rsqrt(double d) {
     return fma(y * e, fma(0.375, e, 0.5), y);             // y (1 + e/2 + 3 e^2/8)
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(addr));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, int parity) {
+    int ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n selp.b32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+// shared-memory accesses that keep their order among themselves but are no barrier for the arithmetic around them
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.volatile.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v));
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+
+#ifdef FGP_POTF2_PROF
+__device__ long long g_potf2_prof[32];
+#define PROF(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_potf2_prof[i] = clock64(); } while (0)
+#else
+#define PROF(i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, long strideW, int* info, int infoOff) {
@@ -52,6 +86,13 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
     double* XP = sm + NB * LDT;           // 32 x 132: XP[k*XLD + row] = staged panel X(row, k)
     double* Eop = XP + SB * XLD;          // 32 x 36 : Eop[k*ELD + n] = E_ss(k, n)
     double* dinvE = Eop + SB * ELD;       // 128: diagonal of L^-1
+    double* rinvS = dinvE + NB + SB;      // 32: 1 / l_jj of the current sub-block (warp 0 -> warp 1)
+    // one mbarrier per column of a sub-block (32 arrivals: the lanes of warp 0), one phase per sub-step
+    const uint32_t barAddr = (uint32_t)__cvta_generic_to_shared(rinvS + SB);
+    if (threadIdx.x < SB) {
+        asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(barAddr + 8 * threadIdx.x), "r"(32));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -60,6 +101,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
     double* Mb = M + (long)blockIdx.x * strideM;
     double* Wb = W + (long)blockIdx.x * strideW + (long)(k0 / NB) * NB * NB;
 
+    PROF(0);
     // ---- load the lower triangle (identity padding for a ragged block, zeros above the diagonal)
     if (nb == NB) {
         // whole 16-byte row pairs, all in flight at once; the strict upper part is cleared afterwards
@@ -93,47 +135,65 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
 
     for (int s = 0; s < NB / SB; ++s) {
         const int o = s * SB;
-        // ================= (a) 32x32 Cholesky + its inverse transpose, warp 0 =================
+        PROF(1 + 3 * s);
+        // ================= (a) 32x32 Cholesky (warp 0) and its inverse transpose (warp 1, one column behind) ========
         if (warp == 0) {
-            double a[SB], e[SB];
+            // No branch, barrier or fence inside the 32 steps: shared memory is touched through volatile asm only, so
+            // that ptxas is free to interleave the trailing updates of step j-1 with the pivot chain of step j.
+            double a[SB];
 #pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                a[j] = T[(o + j) * LDT + o + lane];
-                e[j] = (j == lane) ? 1.0 : 0.0;
-            }
+            for (int j = 0; j < SB; ++j) a[j] = T[(o + j) * LDT + o + lane];
             double dg = T[(o + lane) * LDT + o + lane];
+            int firstBad = 0;
+            const uint32_t tS = (uint32_t)__cvta_generic_to_shared(T + o * LDT + o);   // sub-block origin
+            const uint32_t rS = (uint32_t)__cvta_generic_to_shared(rinvS);
 #pragma unroll
             for (int j = 0; j < SB; ++j) {
                 double d = __shfl_sync(0xffffffffu, dg, j);
-                if (!(d > 0.0)) {   // not positive definite: remember the minor's order, keep going finite
-                    if (lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + j + 1;
-                    d = 1.0;
-                }
+                const bool bad = !(d > 0.0);   // not positive definite: remember the minor's order, keep going finite
+                firstBad = (bad && firstBad == 0) ? j + 1 : firstBad;
+                d = bad ? 1.0 : d;
                 const double rinv = pivot_rsqrt(d);
-                double l = 0.0;
-                if (lane > j) l = a[j] * rinv;
-                else if (lane == j) l = d * rinv;
-                const double x = e[j] * rinv;          // E(lane, j); zero for lane > j
-                e[j] = x;
+                double l = a[j] * rinv;
+                l = lane > j ? l : (lane == j ? d * rinv : 0.0);
                 dg = fma(-l, l, dg);
-                if (lane >= j) T[(o + j) * LDT + o + lane] = l;
+                if (lane >= j) sts_f64(tS + (uint32_t)((j * LDT + lane) * 8), l);
+                if (lane == 0) sts_f64(rS + j * 8, rinv);
                 if (j + 1 < SB) {
                     const double ln = __shfl_sync(0xffffffffu, l, j + 1);
                     a[j + 1] = fma(-l, ln, a[j + 1]);
-                    e[j + 1] = fma(-x, ln, e[j + 1]);
                 }
-                __syncwarp();
+                // column j and 1/l_jj are in shared memory: every lane releases its own stores to warp 1
+                mbar_arrive(barAddr + 8 * j);
                 // column j read back as 16-byte pairs (shared-memory loads are the scarce resource here)
-                if ((j + 2) & 1) {
-                    const double lc = T[(o + j) * LDT + o + j + 2];
-                    if (j + 2 < SB) { a[j + 2] = fma(-l, lc, a[j + 2]); e[j + 2] = fma(-x, lc, e[j + 2]); }
-                }
+                if (((j + 2) & 1) && j + 2 < SB) a[j + 2] = fma(-l, lds_f64(tS + (uint32_t)((j * LDT + j + 2) * 8)), a[j + 2]);
 #pragma unroll
                 for (int c = (j + 3) & ~1; c + 1 < SB; c += 2) {
-                    const double2 lc = *reinterpret_cast<const double2*>(&T[(o + j) * LDT + o + c]);
+                    const double2 lc = lds_v2f64(tS + (uint32_t)((j * LDT + c) * 8));
                     a[c] = fma(-l, lc.x, a[c]);
-                    e[c] = fma(-x, lc.x, e[c]);
                     a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                }
+            }
+            if (firstBad && lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + firstBad;
+        } else if (warp == 1) {
+            // E_ss = L_ss^-T, lane = row of E: E(:, c) -= E(:, j) L(c, j) / ... with the columns warp 0 has released
+            double e[SB];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) e[j] = (j == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                for (int spin = 0; !mbar_try_wait(barAddr + 8 * j, s & 1); ++spin)
+                    if (spin > (1 << 24)) __trap();   // a protocol bug must trap, never hang the device
+                const double x = e[j] * rinvS[j];     // E(lane, j); zero for lane > j
+                e[j] = x;
+                if ((j + 1) & 1) {
+                    const double lc = T[(o + j) * LDT + o + j + 1];
+                    if (j + 1 < SB) e[j + 1] = fma(-x, lc, e[j + 1]);
+                }
+#pragma unroll
+                for (int c = (j + 2) & ~1; c + 1 < SB; c += 2) {
+                    const double2 lc = *reinterpret_cast<const double2*>(&T[(o + j) * LDT + o + c]);
+                    e[c] = fma(-x, lc.x, e[c]);
                     e[c + 1] = fma(-x, lc.y, e[c + 1]);
                 }
             }
@@ -148,6 +208,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
             }
         }
         __syncthreads();
+        PROF(2 + 3 * s);
         // ================= (b) X = B * E_ss for the rows outside the diagonal sub-block, DMMA =================
         {
             const int rbase = warp * 16;                         // this warp's 16 rows (two 8-row blocks)
@@ -187,6 +248,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
             }
         }
         __syncthreads();
+        PROF(3 + 3 * s);
         // ================= (c) rank-32 update of the columns to the right, DMMA =================
         const int c_first = o + SB;
         const int nnb = (NB - c_first) / 8;                       // 8-column blocks to the right: 12, 8, 4, 0
@@ -230,33 +292,27 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
         __syncthreads();
     }
 
+    PROF(13);
     // ---- write back L (lower triangle of the valid part)
 #pragma unroll 8
     for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
         const int r = idx & (NB - 1), c = idx >> 7;
         if (r >= c && r < nb && c < nb) Mb[(long)(k0 + r) + (long)(k0 + c) * ld] = T[c * LDT + r];
     }
-    // ---- W = inv(L) (128x128 column-major, unit padded): W(r,c) = E(c,r) = T(row c, col r) for r > c.
-    //      Transposed through XP (33-stride staging) so that both the shared reads and the global writes are contiguous.
-    double* stage = XP;                                            // 128 x 33 doubles fit (4224 <= 32*132)
-    for (int q = 0; q < NB / SB; ++q) {
-        __syncthreads();
-        // stage[kk*33 + j] = T(row kk, col 32q + j)   (threads walk down kk: contiguous in T)
-        for (int idx = tid; idx < NB * SB; idx += POTF2_THREADS) {
-            const int kk = idx & (NB - 1), j = idx >> 7;
-            stage[kk * 33 + j] = T[(q * SB + j) * LDT + kk];
-        }
-        __syncthreads();
-        // W(r = 32q + j, c = kk): threads walk along j: contiguous in global
-        for (int idx = tid; idx < NB * SB; idx += POTF2_THREADS) {
-            const int j = idx & (SB - 1), kk = idx >> 5;
-            const int r = q * SB + j, c = kk;
-            double w = 0.0;
-            if (r > c) w = stage[kk * 33 + j];
-            else if (r == c) w = dinvE[r];
-            Wb[r + c * NB] = w;
-        }
+    PROF(14);
+    // ---- W = inv(L) (128x128 column-major, unit padded): W(r,c) = E(c,r) = T(row c, col r) for r > c, i.e. T read
+    //      along its leading dimension.  A half-warp takes 4 consecutive r x 4 consecutive c: with LDT = 4 (mod 16) the
+    //      sixteen 8-byte words fall into sixteen different bank pairs, and every 4 r of one c are one 32-byte sector.
+    for (int it = 0; it < (NB * NB) / (POTF2_THREADS * 1); ++it) {
+        const int blk = it * 8 + warp;                      // 32 r-groups x 16 c-groups: 512 blocks of 4 r x 8 c
+        const int r = (blk & 31) * 4 + (lane & 3);
+        const int c = (blk >> 5) * 8 + (lane >> 2);
+        double w = 0.0;
+        if (r > c) w = T[r * LDT + c];
+        else if (r == c) w = dinvE[r];
+        Wb[r + c * NB] = w;
     }
+    PROF(15);
 }
 
 }  // namespace
