@@ -80,6 +80,8 @@ extern "C" int fgp_ctx_create(int n_devices, const int* device_ids, fgp_ctx** ou
 
 extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
     if (!ctx) return;
+    for (fgp_ctx* w : ctx->fitWorkers) fgp_ctx_destroy(w);
+    ctx->fitWorkers.clear();
     for (auto& d : ctx->dev) {
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();

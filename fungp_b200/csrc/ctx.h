@@ -105,6 +105,9 @@ struct fgp_ctx {
     int outer_single = 2;     // same for a single factorisation with look-ahead (its panel chain is exposed)
     double timing[8] = {0};
     std::mutex mu;
+    // fgp_fit_batch: worker contexts (one per device and worker slot), created on first use and kept: creating streams
+    // and workspaces per call cost more than a candidate at n = 1024
+    std::vector<fgp_ctx*> fitWorkers;
 };
 
 struct ProblemDev {

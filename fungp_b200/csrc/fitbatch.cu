@@ -230,19 +230,28 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
     const int wpd = std::max(1, ctx->fit_workers);
     std::vector<std::thread> th;
     std::atomic<int> ctxFail{0};
+    // worker contexts persist in the parent context (slot = device index * 16 + worker)
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->fitWorkers.size() < (size_t)nd * 16) ctx->fitWorkers.resize((size_t)nd * 16, nullptr);
+    }
     for (int dI = 0; dI < nd; ++dI)
         for (int w = 0; w < wpd; ++w) {
             const int device = ctx->dev[dI].device;
-            th.emplace_back([&, device]() {
-                fgp_ctx* wc = nullptr;
-                if (fgp_ctx_create(1, &device, &wc) != 0) { ctxFail++; return; }
+            fgp_ctx** slot = &ctx->fitWorkers[(size_t)dI * 16 + w];
+            th.emplace_back([&, device, slot]() {
+                if (!*slot && fgp_ctx_create(1, &device, slot) != 0) { *slot = nullptr; ctxFail++; return; }
+                fgp_ctx* wc = *slot;
+                cudaSetDevice(device);
                 wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
                 for (;;) {
                     const int item = S.next.fetch_add(1);
                     if (item >= n_items) break;
                     fit_one(S, wc, item);
                 }
-                fgp_ctx_destroy(wc);
+                // large workspaces go back to the device (candidates at n = 8192 need GBs per worker); small ones stay
+                DevState& d = wc->dev[0];
+                if (d.work.cap + d.wbuf.cap > ((size_t)2 << 30)) { d.work.release(); d.wbuf.release(); }
             });
         }
     for (auto& t : th) t.join();

@@ -359,3 +359,25 @@ def test_c5_size_properties(ctx):
     assert np.max(np.abs(mu_t - ya[idx])) <= 1e-3 * (np.max(ya) - np.min(ya))
     assert np.max(sd_t) <= 1e-2 * sd0
     P.close()
+
+
+def test_rank_deficient_gram_matrix(ctx):
+    """L2_bygroup with a Gram matrix that is only positive SEMI-definite (a basis with dependent columns): the
+    Cholesky whitening of csrc/api.cu falls back to the eigen-decomposition; distances and the likelihood still
+    follow the reference's bilinear form (c_i - c_j)' J (c_i - c_j) (R/7_distanceFunctions.R:39-45)."""
+    import fungp_b200
+    rng = np.random.default_rng(21)
+    n, p = 200, 4
+    A = rng.standard_normal((2, p))
+    J = A.T @ A                                  # rank 2
+    coefs = rng.standard_normal((n, p))
+    y = np.sin(coefs @ A[0]) + 0.1 * rng.standard_normal(n)
+    P = fungp_b200.Problem(ctx, None, [coefs], [J], ["L2_bygroup"], y)
+    D = P.dist_matrix(0)
+    Dr = ref.setDistMatrix_F([coefs], [coefs], [J], ["L2_bygroup"])[0]
+    assert np.max(np.abs(D - Dr)) <= 1e-12 * np.max(Dr) * 10
+    theta = np.array([0.4 * Dr.max()])
+    nll, sig2, info = P.nll_batch("matern5_2", 1e-6, theta)
+    r_nll, r_s2 = ref.negLogLik(theta, [], [Dr], y, "matern5_2", 1e-6)
+    assert info[0] == 0 and abs(nll[0] - r_nll) <= _nll_tol(r_nll, n, _noise_floor(theta, [Dr], y, "matern5_2", 1e-6))
+    P.close()
