@@ -159,6 +159,9 @@ def run_ours(args):
     ctx = fungp_b200.Context(device_ids=[local_rank])
     ctx.set_option("streams", args.streams)
     ctx.set_option("outer", args.outer)
+    ctx.set_option("fit_blocking", args.fit_blocking)
+    if args.fit_workers > 0:
+        ctx.set_option("fit_workers", args.fit_workers)
     sIn, fIn, y = build_inputs()
     n, ker, nug = CFG["n"], CFG["ker"], CFG["nugget"]
     proj = [ctx.project(f, p, CFG["basis"]) for f, p in zip(fIn, CFG["pdims"])]
@@ -419,6 +422,8 @@ def main():
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--outer", type=int, default=16)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--fit-workers", type=int, default=0, help="fit_batch worker contexts per GPU (0 = library default, 8)")
+    ap.add_argument("--fit-blocking", type=int, default=-1, help="fit_batch workers: 1 sleep / 0 spin in host waits, -1 auto")
     ap.add_argument("--factory-cands", type=int, default=48, help="candidate structures per GPU for the factory metric (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

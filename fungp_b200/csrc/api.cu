@@ -26,6 +26,20 @@ void fgp_set_err_cuda(fgp_ctx* ctx, const char* what, cudaError_t e, const char*
         }                                                                     \
     } while (0)
 
+// Host wait for a stream.  Worker contexts of fgp_fit_batch (blockingSync) sleep on an event created with
+// cudaEventBlockingSync instead of spinning: 8 workers per GPU on an 8-GPU box are 64 waiting threads, more than the
+// box has cores.  User contexts keep the lower-latency spin of cudaStreamSynchronize.
+static cudaError_t wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st) {
+    if (!ctx->blockingSync) return cudaStreamSynchronize(st);
+    if (!d.evWait) {
+        cudaError_t e = cudaEventCreateWithFlags(&d.evWait, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(d.evWait, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(d.evWait);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long roundup(long a, long b) { return (a + b - 1) / b * b; }
 // leading dimension: multiple of 16 doubles (128 B); avoid large power-of-two strides
@@ -92,6 +106,7 @@ extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
         if (d.sBulk) cudaStreamDestroy(d.sBulk);
         if (d.evA) cudaEventDestroy(d.evA);
         if (d.evB) cudaEventDestroy(d.evB);
+        if (d.evWait) cudaEventDestroy(d.evWait);
         d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release(); d.pool.release();
         if (d.pinned) cudaFreeHost(d.pinned);
     }
@@ -105,6 +120,8 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     if (!ctx || !name) return FGP_ERR_ARG;
     if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
+    else if (!strcmp(name, "fit_blocking")) ctx->fit_blocking = value < 0 ? -1 : (value != 0);
+    else if (!strcmp(name, "blocking_sync")) ctx->blockingSync = value != 0;
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(1, std::min((int)value, 16));
@@ -267,7 +284,7 @@ int problem_upload(fgp_problem* P, int slot) {
     CK(cudaMemcpyAsync(pd.X, P->X.data(), sizeof(double) * P->X.size(), cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(pd.units, P->units.data(), sizeof(FgpUnit) * P->units.size(), cudaMemcpyHostToDevice, up));
     CK(cudaMemcpyAsync(pd.y, P->y.data(), sizeof(double) * P->n, cudaMemcpyHostToDevice, up));
-    CK(cudaStreamSynchronize(up));
+    CK(wait_stream(ctx, ctx->dev[slot], up));
     pd.ready = true;
     return 0;
 }
@@ -344,7 +361,7 @@ extern "C" int fgp_problem_set_y(fgp_problem* P, const double* y) {
         if (P->pd[s].ready) {
             CK(cudaSetDevice(ctx->dev[s].device));
             CK(cudaMemcpyAsync(P->pd[s].y, y, sizeof(double) * P->n, cudaMemcpyHostToDevice, ctx->dev[s].sPanel[0]));
-            CK(cudaStreamSynchronize(ctx->dev[s].sPanel[0]));
+            CK(wait_stream(ctx, ctx->dev[s], ctx->dev[s].sPanel[0]));
         }
     P->hasModel = false;
     return 0;
@@ -367,7 +384,7 @@ extern "C" int fgp_dist_max(fgp_problem* P, double* max_out) {
     }
     std::vector<double> h(P->nterms);
     CK(cudaMemcpyAsync(h.data(), dmax, sizeof(double) * P->nterms, cudaMemcpyDeviceToHost, d.sPanel[0]));
-    CK(cudaStreamSynchronize(d.sPanel[0]));
+    CK(wait_stream(ctx, d, d.sPanel[0]));
     for (int t = 0; t < P->nterms; ++t) {
         const FgpUnit& u = P->units[P->termFirstUnit[t]];
         if (u.kind == 1) max_out[t] = h[t];
@@ -392,7 +409,7 @@ extern "C" int fgp_dist_materialize(fgp_problem* P, int l, double* out) {
     launch_distmat(P->pd[0].X, n, n, P->pd[0].units, P->termFirstUnit[l], P->termFirstUnit[l + 1], (double*)d.work.p, n,
                    d.sPanel[0]);
     CK(cudaMemcpyAsync(out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, d.sPanel[0]));
-    CK(cudaStreamSynchronize(d.sPanel[0]));
+    CK(wait_stream(ctx, d, d.sPanel[0]));
     return 0;
 }
 
@@ -424,7 +441,7 @@ extern "C" int fgp_assemble(fgp_problem* P, int ker, double nugget, const double
     launch_assemble(a, 1, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(R_out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, d, st));
     return 0;
 }
 
@@ -513,7 +530,7 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             if (prof) { d.timers.cur = fa; d.timers.end(st, FgpTimers::FACTOR, 0.0); }
             launch_nll_reduce(Mg, ld, (long)ld * n, gb, n, n, var_known ? dVar : nullptr, dInfo + g0, dNll + g0, dSig + g0, st);
         }
-        for (int s = 0; s < ns; ++s) CK(cudaStreamSynchronize(d.sPanel[s]));
+        for (int s = 0; s < ns; ++s) CK(wait_stream(ctx, d, d.sPanel[s]));
         CK(cudaGetLastError());
         CK(cudaMemcpy(nll + b0 + c0, dNll, sizeof(double) * cb, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(sig2 + b0 + c0, dSig, sizeof(double) * cb, cudaMemcpyDeviceToHost));
@@ -581,7 +598,7 @@ extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, 
     if (rc) return rc;
     int hinfo = 0;
     CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, d, st));
     CK(cudaGetLastError());
     if (hinfo != 0) { P->hasModel = false; return hinfo; }
     P->hasModel = true; P->ker = ker; P->nugget = nugget; P->sig2 = sig2;
@@ -592,7 +609,7 @@ extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, 
         if (d.work.ensure(sizeof(double) * (size_t)n * n)) return FGP_ERR_ALLOC;
         launch_extract_lower(pd.Lfac, ld, n, (double*)d.work.p, st);
         CK(cudaMemcpyAsync(L_out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(wait_stream(ctx, d, st));
     }
     return 0;
 }
@@ -608,7 +625,7 @@ static int upload_new(fgp_problem* P, DevState& d, int m, const double* sNew, co
     build_coords(P, m, sNew, coefsNew, X);
     if (d.aux.ensure(sizeof(double) * std::max<size_t>(1, X.size()))) return FGP_ERR_ALLOC;
     CK(cudaMemcpyAsync(d.aux.p, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice, d.sPanel[0]));
-    CK(cudaStreamSynchronize(d.sPanel[0]));
+    CK(wait_stream(ctx, d, d.sPanel[0]));
     *Xnew_dev = (double*)d.aux.p;
     return 0;
 }
@@ -664,7 +681,7 @@ extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const doub
     std::vector<double> hn(m);
     CK(cudaMemcpyAsync(mean, dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, d, st));
     CK(cudaGetLastError());
     for (int i = 0; i < m; ++i) sd[i] = sqrt(std::max(P->sig2 - hn[i], 0.0));
     if (detail == FGP_DETAIL_FULL) {
@@ -675,7 +692,7 @@ extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const doub
             b.M = (double*)d.work.p; b.ld = n; b.rowOff = 0; b.colOff = 0;
             launch_assemble(b, 1, st);
             CK(cudaMemcpyAsync(Ktp, d.work.p, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(wait_stream(ctx, d, st));
         }
         if (Kpp) {   // m x m, sig2 * (R_pp + nugget I)      (R/4_prediction_SF.R:16-17)
             if (d.work.ensure(sizeof(double) * (size_t)m * m)) return FGP_ERR_ALLOC;
@@ -684,7 +701,7 @@ extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const doub
             b.diag_rel = P->nugget; b.M = (double*)d.work.p; b.ld = m; b.rowOff = 0; b.colOff = 0;
             launch_assemble(b, 1, st);
             CK(cudaMemcpyAsync(Kpp, d.work.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(wait_stream(ctx, d, st));
         }
         CK(cudaGetLastError());
     }
@@ -753,7 +770,7 @@ extern "C" int fgp_simulate(fgp_problem* P, int m, const double* sNew, const dou
     CK(cudaMemcpyAsync(hm.data(), dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(sims, dSims, sizeof(double) * (size_t)m * nsim, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, d, st));
     CK(cudaGetLastError());
     if (hinfo != 0) return hinfo;    // chol(K.ss - ...) failed: base R's error (quirk Q5)
     if (mean) memcpy(mean, hm.data(), sizeof(double) * m);
@@ -808,7 +825,7 @@ extern "C" int fgp_loocv(fgp_problem* P, double* y_pre, double* q2) {
     CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hd.data(), dDiag, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hr.data(), dRy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(wait_stream(ctx, d, st));
     CK(cudaGetLastError());
     if (hinfo != 0) return hinfo;
     // y_pre = y - Rinv y / diag(Rinv)  (R/8_outilsStats.R:6);  Q2 = 1 - mean((y-yhat)^2)/mean((y-ybar)^2)

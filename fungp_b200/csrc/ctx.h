@@ -83,6 +83,7 @@ struct DevState {
     cudaStream_t sPanel[MAXSTREAMS] = {nullptr};
     cudaStream_t sBulk = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr, evJoin[MAXSTREAMS] = {nullptr}, evMark[4] = {nullptr};
+    cudaEvent_t evWait = nullptr;   // blocking-sync event of wait_stream (fit_batch workers)
     DevBuf work;      // factorisation workspaces (batch of trapezoids)
     DevBuf wbuf;      // inverse diagonal blocks
     DevBuf small;     // thetas / scales / results
@@ -101,6 +102,8 @@ struct fgp_ctx {
     int lookahead = 1;
     int streams = 8;
     int fit_workers = 8;      // fgp_fit_batch: concurrent candidate fits per GPU
+    int blockingSync = 0;     // host waits sleep instead of spinning (set on fit_batch worker contexts)
+    int fit_blocking = -1;    // option "fit_blocking": worker contexts of fgp_fit_batch use blocking waits (-1 = auto)
     int outer = 16;           // column tiles per outer panel for batches (trailing update K = outer*128)
     int outer_single = 2;     // same for a single factorisation with look-ahead (its panel chain is exposed)
     double timing[8] = {0};

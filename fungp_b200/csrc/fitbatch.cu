@@ -228,8 +228,34 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
     const int n_items = n_cand * std::max(1, n_rep);
     const int nd = (int)ctx->dev.size();
     const int wpd = std::max(1, ctx->fit_workers);
+    // Longest first: the cost of a fit grows with its number of length-scales (finite-difference batch = 2d + 1 and
+    // more L-BFGS-B iterations), so the queue hands out the big structures first and the small ones fill the tail.
+    // Results are written per item, so the order of the outputs does not change.
+    std::vector<int> order(n_items), nls(n_items, 0);
+    for (int it = 0; it < n_items; ++it) {
+        order[it] = it;
+        const int* ant = ants + (size_t)(it / std::max(1, n_rep)) * S.antLen;
+        int d = 0;
+        for (int i = 0; i < ds; ++i) d += ant[i] == 1;
+        for (int j = 0; j < df; ++j) {
+            const int* a = ant + ds + 4 * j;
+            if (a[0] != 1) continue;
+            d += a[1] == FGP_DIST_BYINDEX ? (a[2] > 0 ? a[2] : k[j]) : 1;
+        }
+        nls[it] = d;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nls[a] > nls[b]; });
     std::vector<std::thread> th;
     std::atomic<int> ctxFail{0};
+    // Spin or sleep in the workers' host waits?  Spinning is ~6 % faster while every waiting thread has a core; assume
+    // every visible GPU of the node runs as many workers as this call (one process per GPU under torchrun)
+    int blocking = ctx->fit_blocking;
+    if (blocking < 0) {
+        int visible = 1;
+        if (cudaGetDeviceCount(&visible) != cudaSuccess) { cudaGetLastError(); visible = 1; }
+        const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+        blocking = (unsigned)(wpd * std::max(visible, nd)) * 4u > cores * 3u;
+    }
     // worker contexts persist in the parent context (slot = device index * 16 + worker)
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -239,15 +265,16 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
         for (int w = 0; w < wpd; ++w) {
             const int device = ctx->dev[dI].device;
             fgp_ctx** slot = &ctx->fitWorkers[(size_t)dI * 16 + w];
-            th.emplace_back([&, device, slot]() {
+            th.emplace_back([&, device, slot, blocking]() {
                 if (!*slot && fgp_ctx_create(1, &device, slot) != 0) { *slot = nullptr; ctxFail++; return; }
                 fgp_ctx* wc = *slot;
                 cudaSetDevice(device);
                 wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
+                wc->blockingSync = blocking;
                 for (;;) {
-                    const int item = S.next.fetch_add(1);
-                    if (item >= n_items) break;
-                    fit_one(S, wc, item);
+                    const int q = S.next.fetch_add(1);
+                    if (q >= n_items) break;
+                    fit_one(S, wc, order[q]);
                 }
                 // large workspaces go back to the device (candidates at n = 8192 need GBs per worker); small ones stay
                 DevState& d = wc->dev[0];
