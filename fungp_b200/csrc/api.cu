@@ -473,22 +473,37 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
         fgp_set_err(ctx, "fgp_nll_batch: out of device memory");
         return FGP_ERR_ALLOC;
     }
-    // small buffer: scales [chunk*nt] | nll [chunk] | sig2 [chunk] | var_known [1] | info [chunk]
-    const size_t smallBytes = sizeof(double) * ((size_t)chunk * nt + 2 * (size_t)chunk + 1) + sizeof(int) * chunk;
+    // small buffer: scales [chunk*nt] | nll [chunk] | sig2 [chunk] | info [chunk ints, padded] | var_known [1]
+    const size_t resBytes = sizeof(double) * 2 * (size_t)chunk + sizeof(int) * (size_t)roundup(chunk, 2);
+    const size_t smallBytes = sizeof(double) * ((size_t)chunk * nt + 1) + resBytes;
     if (d.small.ensure(smallBytes)) return FGP_ERR_ALLOC;
     double* dScale = (double*)d.small.p;
     double* dNll = dScale + (size_t)chunk * nt;
     double* dSig = dNll + chunk;
-    double* dVar = dSig + chunk;
-    int* dInfo = (int*)(dVar + 1);
-    std::vector<double> hScale((size_t)chunk * nt);
+    int* dInfo = (int*)(dSig + chunk);
+    double* dVar = (double*)((char*)dNll + resBytes);
+    // pinned staging for the length-scale multipliers (H2D) and the results (one D2H per chunk): the copies are truly
+    // asynchronous, so the only host wait of the call is wait_stream below
+    const size_t pinBytes = sizeof(double) * (size_t)chunk * nt + resBytes;
+    if (pinBytes > d.pinnedCap) {
+        if (d.pinned) cudaFreeHost(d.pinned);
+        d.pinned = nullptr; d.pinnedCap = 0;
+        if (cudaHostAlloc(&d.pinned, std::max<size_t>(pinBytes, 1 << 16), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            fgp_set_err(ctx, "fgp_nll_batch: out of pinned host memory");
+            return FGP_ERR_ALLOC;
+        }
+        d.pinnedCap = std::max<size_t>(pinBytes, 1 << 16);
+    }
+    double* hScale = (double*)d.pinned;
+    char* hRes = (char*)d.pinned + sizeof(double) * (size_t)chunk * nt;
     const bool prof = ctx->profile != 0;
     if (prof) d.timers.reset();
     const double hVar = var_known ? *var_known : 0.0;
 
     for (int c0 = 0; c0 < B; c0 += chunk) {
         const int cb = std::min(chunk, B - c0);
-        for (int i = 0; i < cb; ++i) kernel_scales(ker, nt, thetas + (size_t)(b0 + c0 + i) * nt, &hScale[(size_t)i * nt]);
+        for (int i = 0; i < cb; ++i) kernel_scales(ker, nt, thetas + (size_t)(b0 + c0 + i) * nt, hScale + (size_t)i * nt);
         // NOTE: every host->device copy below is issued on the stream that consumes it.  The library's streams are
         // non-blocking: they do not wait for the legacy default stream, and a cudaMemcpy from pageable memory may return
         // before its DMA has landed -- kernels on another stream would then read the previous batch's length-scales
@@ -507,7 +522,7 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             const int gb = g1 - g0;
             cudaStream_t st = d.sPanel[s];
             double* Mg = (double*)d.work.p + (size_t)g0 * ld * n;
-            CK(cudaMemcpyAsync(dScale + (size_t)g0 * nt, hScale.data() + (size_t)g0 * nt, sizeof(double) * (size_t)gb * nt,
+            CK(cudaMemcpyAsync(dScale + (size_t)g0 * nt, hScale + (size_t)g0 * nt, sizeof(double) * (size_t)gb * nt,
                                cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(dInfo + g0, 0, sizeof(int) * gb, st));
             if (var_known) CK(cudaMemcpyAsync(dVar, &hVar, sizeof(double), cudaMemcpyHostToDevice, st));
@@ -530,11 +545,18 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             if (prof) { d.timers.cur = fa; d.timers.end(st, FgpTimers::FACTOR, 0.0); }
             launch_nll_reduce(Mg, ld, (long)ld * n, gb, n, n, var_known ? dVar : nullptr, dInfo + g0, dNll + g0, dSig + g0, st);
         }
-        for (int s = 0; s < ns; ++s) CK(wait_stream(ctx, d, d.sPanel[s]));
+        // join the groups on stream 0, fetch nll | sig2 | info with one copy, and wait once
+        for (int s = 1; s < ns; ++s) {
+            if (!d.evJoin[s]) CK(cudaEventCreateWithFlags(&d.evJoin[s], cudaEventDisableTiming));
+            CK(cudaEventRecord(d.evJoin[s], d.sPanel[s]));
+            CK(cudaStreamWaitEvent(d.sPanel[0], d.evJoin[s], 0));
+        }
+        CK(cudaMemcpyAsync(hRes, dNll, resBytes, cudaMemcpyDeviceToHost, d.sPanel[0]));
+        CK(wait_stream(ctx, d, d.sPanel[0]));
         CK(cudaGetLastError());
-        CK(cudaMemcpy(nll + b0 + c0, dNll, sizeof(double) * cb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(sig2 + b0 + c0, dSig, sizeof(double) * cb, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(info + b0 + c0, dInfo, sizeof(int) * cb, cudaMemcpyDeviceToHost));
+        memcpy(nll + b0 + c0, hRes, sizeof(double) * cb);
+        memcpy(sig2 + b0 + c0, hRes + sizeof(double) * chunk, sizeof(double) * cb);
+        memcpy(info + b0 + c0, hRes + sizeof(double) * 2 * chunk, sizeof(int) * cb);
     }
     return 0;
 }
