@@ -1,6 +1,7 @@
 // C ABI of libfungp_b200.so (include/fungp_b200.h): contexts, problems and the likelihood / prediction /
 // simulation / LOOCV entry points.  No CPU fallback: every numeric path launches the sm_100a kernels.
 #include "ctx.h"
+#include <sched.h>
 #include "../../include/fungp_b200.h"
 #include <cstring>
 #include <thread>
@@ -37,6 +38,15 @@ static cudaError_t wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st) {
     }
     cudaError_t e = cudaEventRecord(d.evWait, st);
     if (e != cudaSuccess) return e;
+    if (ctx->blockingSync == 2) {
+        // poll and yield: next to no added latency while a core is free, and waiting threads give way when there are
+        // more of them than cores
+        for (;;) {
+            e = cudaEventQuery(d.evWait);
+            if (e != cudaErrorNotReady) return e;
+            sched_yield();
+        }
+    }
     return cudaEventSynchronize(d.evWait);
 }
 
@@ -120,8 +130,8 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     if (!ctx || !name) return FGP_ERR_ARG;
     if (!strcmp(name, "profile")) ctx->profile = value != 0;
     else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
-    else if (!strcmp(name, "fit_blocking")) ctx->fit_blocking = value < 0 ? -1 : (value != 0);
-    else if (!strcmp(name, "blocking_sync")) ctx->blockingSync = value != 0;
+    else if (!strcmp(name, "fit_blocking")) ctx->fit_blocking = value < 0 ? -1 : std::min((int)value, 2);
+    else if (!strcmp(name, "blocking_sync")) ctx->blockingSync = std::max(0, std::min((int)value, 2));
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(1, std::min((int)value, 16));

@@ -151,9 +151,9 @@ int fgp_mark(fgp_ctx* ctx, int idx);
 int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
 /* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU),
  * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128), "fit_workers" (1..16),
- * "fit_blocking" (0/1/-1: the worker contexts of fgp_fit_batch sleep in their host waits instead of spinning; default
- * -1 = sleep when workers x visible GPUs exceed 3/4 of the host cores),
- * "blocking_sync" (0/1, default 0: the same for this context's own calls). */
+ * "fit_blocking" (host waits of the fgp_fit_batch worker contexts: 0 spin, 1 sleep on a blocking event, 2 poll and yield;
+ * default -1 = yield when workers x visible GPUs exceed 3/4 of the host cores, else spin),
+ * "blocking_sync" (0/1/2, default 0: the same for this context's own calls). */
 int fgp_set_option(fgp_ctx* ctx, const char* name, double value);
 /* measured FP64 peaks on device 0 for the roofline denominators: register-resident DMMA (m8n8k4) loop and
  * DFMA loop, TFLOP/s; and a device copy, GB/s. */

@@ -11,7 +11,7 @@ ctx = fungp_b200.Context(1)
 sIn, fIn, y = synth.make_data(1024, 1024, 5, [10, 22, 50])
 ants = bench.factory_candidates(96)
 base = None
-for w, blk in ((8, 1), (8, 0), (8, 1), (8, 0), (12, 1), (16, 1)):
+for w, blk in ((8, 2), (8, 0), (8, 2), (8, 1), (16, 2)):
     ctx.set_option("fit_blocking", blk)
     ctx.set_option("fit_workers", w)
     t0 = time.perf_counter()
