@@ -127,12 +127,17 @@ def run_factory(ctx, rank, world, cands_per_gpu, barrier):
     ants = factory_candidates(cands_per_gpu * world)
     mine = ants[rank::world]            # round-robin deal: candidate costs vary with the structure, this evens them out
     F.score_candidates(ctx, sIn, fIn, y, mine[:8], NumpyRng(0), nugget=FACTORY["nugget"])       # warm-up (one per worker)
-    barrier()
-    t0 = time.perf_counter()
-    res = F.score_candidates(ctx, sIn, fIn, y, mine, NumpyRng(rank + 1), nugget=FACTORY["nugget"],
-                             n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"])
-    barrier()
-    return time.perf_counter() - t0, len(ants), int((res["info"] == 0).sum()), float(np.nanmax(res["fitness"]))
+    # three repetitions of the same generation; the median is reported (host scheduling noise on shared boxes moves a
+    # 2-second measurement by +-20 %), all three are listed
+    times = []
+    for rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        res = F.score_candidates(ctx, sIn, fIn, y, mine, NumpyRng(rank + 1), nugget=FACTORY["nugget"],
+                                 n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"])
+        barrier()
+        times.append(time.perf_counter() - t0)
+    return times, len(ants), int((res["info"] == 0).sum()), float(np.nanmax(res["fitness"]))
 
 
 def build_inputs(rank=0):
@@ -230,12 +235,12 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     wall, dev_ms, wall_e2e = [float(x) for x in tt.cpu()]
     if fac is not None:
-        ft = torch.tensor([fac[0]], dtype=torch.float64)
+        ft = torch.tensor(fac[0], dtype=torch.float64)
         fo = torch.tensor([float(fac[2])], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ft, op=dist.ReduceOp.MAX)
             dist.all_reduce(fo, op=dist.ReduceOp.SUM)
-        fac = (float(ft.item()), fac[1], int(fo.item()), fac[3])
+        fac = ([float(x) for x in ft], fac[1], int(fo.item()), fac[3])
     total_evals = world * B * args.steps
     # the step ends with a host-synchronous read of its results, so wall time >= device time; report the wall clock
     value = total_evals / wall
@@ -315,8 +320,10 @@ def run_ours(args):
             "nll_check": float(nll_last[0]),
         }
         if fac is not None:
-            out["factory"] = {"metric": "fgpm_factory candidates/sec", "value": fac[1] / fac[0], "unit": "candidates/s",
-                              "candidates": fac[1], "fitted_ok": fac[2], "seconds": fac[0], "n_gpus": world,
+            fsec = sorted(fac[0])[len(fac[0]) // 2]      # median repetition (each already the max over ranks)
+            out["factory"] = {"metric": "fgpm_factory candidates/sec", "value": fac[1] / fsec, "unit": "candidates/s",
+                              "candidates": fac[1], "fitted_ok": fac[2], "seconds": fsec,
+                              "runs_candidates_per_s": [fac[1] / t for t in fac[0]], "n_gpus": world,
                               "config": "BASELINE.json configs[3] sizes: n=1024, 5 scalar + 3 functional (len 10/22/50) candidate "
                                         "structures from a fixed pre-generated list, full fit (presample 20, L-BFGS-B, preMats) + "
                                         "Q2loocv per candidate via fgp_fit_batch; candidates sharded over ranks, no collective"}
