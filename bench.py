@@ -281,9 +281,13 @@ def run_ours(args):
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
-        traffic = None
+        traffic, traffic_note = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["update_kernel_dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tj["update_kernel_dram_bytes_per_launch"]
+            traffic_note = ("ncu capture of the K=2048 top-level update launch: %.1f GFLOP, %.1f MB algorithmic, %.1f TFLOP/s and DMMA "
+                            "pipe %.1f %% active under ncu" % (tj["flops_per_launch"] / 1e9, tj["algorithmic_bytes_per_launch"] / 1e6,
+                                                               tj["tflops_under_ncu"], tj["dmma_pipe_active_pct"]))
         except Exception:
             pass
         chol_flops = n ** 3 / 3.0
@@ -304,7 +308,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (trailing update of the blocked Cholesky, FP64 DMMA m8n8k4)",
                          "achieved": upd_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": upd_tf / fp64_peak,
-                         "traffic": traffic,
+                         "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": peak_src + "; MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = 37.2 TFLOP/s "
                                         "at 1965 MHz",
                          "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
