@@ -134,7 +134,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "blocking_sync")) ctx->blockingSync = std::max(0, std::min((int)value, 2));
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
-    else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(1, std::min((int)value, 16));
+    else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(0, std::min((int)value, 16));
     else if (!strcmp(name, "streams")) ctx->streams = std::max(1, std::min((int)value, (int)DevState::MAXSTREAMS));
     else { fgp_set_err(ctx, std::string("unknown option ") + name); return FGP_ERR_ARG; }
     return 0;

@@ -33,7 +33,11 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     const int colSegTile = (t.colHoleLo < t.ncols) ? t.colHoleHi / NBk : ncT;   // first tile of the second column segment
     FgpTimers* tm = ctx->profile ? &ctx->dev[devslot].timers : nullptr;
     const bool la_pre = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;
-    const int outer = std::max(1, la_pre ? ctx->outer_single : ctx->outer);
+    // Look-ahead path: the panel chain of one outer panel (outer x ~110 us) must hide under the trailing update of the
+    // previous one.  Measured (tools/single_probe*.py): n = 8192 best with 2 tiles per panel (10.1 ms; 4: 10.2), n = 16384
+    // with 8 (53.9 ms; 2: 58.8), n = 32768 with 16 (372 ms = 31.5 TFLOP/s; 2: 432)
+    const int outerSingle = ctx->outer_single > 0 ? ctx->outer_single : (ncT < 96 ? 2 : (ncT < 192 ? 8 : 16));
+    const int outer = std::max(1, la_pre ? outerSingle : ctx->outer);
     (void)colHole;
 
     auto col_nb = [&](int k) {

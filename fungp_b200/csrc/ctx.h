@@ -105,7 +105,7 @@ struct fgp_ctx {
     int blockingSync = 0;     // host waits sleep instead of spinning (set on fit_batch worker contexts)
     int fit_blocking = -1;    // option "fit_blocking": worker contexts of fgp_fit_batch use blocking waits (-1 = auto)
     int outer = 16;           // column tiles per outer panel for batches (trailing update K = outer*128)
-    int outer_single = 2;     // same for a single factorisation with look-ahead (its panel chain is exposed)
+    int outer_single = 0;     // same for a single factorisation with look-ahead; 0 = by size (chol.cu)
     double timing[8] = {0};
     std::mutex mu;
     // fgp_fit_batch: worker contexts (one per device and worker slot), created on first use and kept: creating streams

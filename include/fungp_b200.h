@@ -150,7 +150,8 @@ long long fgp_launch_count(void);
 int fgp_mark(fgp_ctx* ctx, int idx);
 int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
 /* options: "profile" (0/1), "lookahead" (0/1), "streams" (1..8 concurrent factorisations per GPU),
- * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128), "fit_workers" (1..16),
+ * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128), "outer_single" (the same for the look-ahead
+ * path of a single factorisation; 0 = chosen by size: 2 below n = 12288, 8 below 24576, else 16), "fit_workers" (1..16),
  * "fit_blocking" (host waits of the fgp_fit_batch worker contexts: 0 spin, 1 sleep on a blocking event, 2 poll and yield;
  * default -1 = yield when workers x visible GPUs exceed 3/4 of the host cores, else spin),
  * "blocking_sync" (0/1/2, default 0: the same for this context's own calls). */
