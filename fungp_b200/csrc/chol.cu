@@ -104,8 +104,16 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
         }
         if (S.hi2 > S.lo2) {
             if (S.lo2 >= cHi) { g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2; }
-            else {
-                // simulate, prefactored steps: extra rows x (train columns: rectangle) + (new columns: triangle)
+            else if (cLo >= S.lo2) {
+                // simulate, prefactored steps, column range inside the new-point block (the look-ahead split hands the
+                // panel stream [cLo, cHi) with cHi < ncT): its triangle plus the extra rows below it
+                g.tri0 = cLo; g.triT = cHi - cLo;
+                g.rectC0 = cLo; g.rectNC = cHi - cLo;
+                g.rectR1 = cHi; g.rectNR1 = std::max(0, S.hi2 - cHi);
+            } else {
+                // simulate, prefactored steps: extra rows x (train columns: rectangle) + (new columns: triangle up to the
+                // last row -- only valid when the range runs to the end, which the callers guarantee: panels and
+                // look-ahead ranges never straddle the boundary between the two column segments)
                 g.rectNC = std::max(0, std::min(cHi, S.lo2) - cLo);
                 g.rectR1 = S.lo2; g.rectNR1 = S.hi2 - S.lo2;
                 if (cHi > S.lo2) { g.tri0 = std::max(S.lo2, cLo); g.triT = cHi - g.tri0; }

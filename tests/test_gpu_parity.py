@@ -165,6 +165,10 @@ PRED_CASES = [
     (22, 300, 50, 2, [20], [4], ["B-splines"], ["L2_byindex"], "matern3_2", 0.4),
     (23, 1000, 130, 3, [30, 40], [5, 3], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "gauss", 0.15),
     (24, 1280, 256, 2, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], "matern5_2", 0.5),
+    # more new points than an outer panel is wide: the look-ahead split of the last prefactored panel's update lands
+    # inside the new-point block (the case that was wrong before the fix in csrc/chol.cu make_update)
+    (25, 640, 700, 2, [30], [4], ["B-splines"], ["L2_bygroup"], "matern5_2", 0.4),
+    (26, 1100, 1000, 1, [40, 20], [3, 4], ["PCA", "B-splines"], ["L2_bygroup", "L2_byindex"], "matern3_2", 0.3),
 ]
 
 
@@ -380,4 +384,38 @@ def test_rank_deficient_gram_matrix(ctx):
     nll, sig2, info = P.nll_batch("matern5_2", 1e-6, theta)
     r_nll, r_s2 = ref.negLogLik(theta, [], [Dr], y, "matern5_2", 1e-6)
     assert info[0] == 0 and abs(nll[0] - r_nll) <= _nll_tol(r_nll, n, _noise_floor(theta, [Dr], y, "matern5_2", 1e-6))
+    P.close()
+
+
+def test_simulate_predict_independent_of_schedule(ctx):
+    """predict / simulate must not depend on how the factorisation is scheduled: outer panel width of the look-ahead
+    path (2, 4, 8, by size) and look-ahead on / off give the same numbers, and they match the oracle."""
+    seed, n, m = 31, 900, 1300
+    case = make_case(seed, n, 2, [30, 30], [4, 3], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], extra=m)
+    Ms = oracle_dists(case)
+    tp, pp = oracle_dists(case, new=True)
+    theta = theta_frac(Ms, 0.35)
+    ker, nug, nsm = "matern5_2", 1e-8, 1e-8
+    _, sig2 = ref.negLogLik(theta, [], Ms, case["y"], ker, nug)
+    L_ref, z_ref = ref.preMats(Ms, case["y"], sig2, theta, ker, nug)
+    Z = np.random.default_rng(seed).standard_normal((m, 5))
+    sm_ref = ref.makeSims(tp, pp, sig2, theta, ker, L_ref, z_ref, Z, nsm, "full")
+    scale = max(1.0, np.max(np.abs(sm_ref["sims"])))
+    P = _problem(ctx, case)
+    P.premats(ker, nug, sig2, theta, want_L=False)
+    base = None
+    try:
+        for la, outer in ((1, 2), (1, 4), (1, 8), (1, 0), (0, 0)):
+            ctx.set_option("lookahead", la); ctx.set_option("outer_single", outer)
+            sm = P.simulate(m, Z, case["sNew"], case["coefsNew"], nugget_sm=nsm)
+            pr = P.predict(m, case["sNew"], case["coefsNew"])
+            err = float(np.max(np.abs(sm["sims"] - sm_ref["sims"])))
+            _log("schedule_invariance", lookahead=la, outer_single=outer, sims_err=err)
+            assert err <= 1e-6 * scale, (la, outer, err)
+            assert np.max(np.abs(pr["mean"] - sm_ref["mean"])) <= 1e-8 * scale
+            if base is None:
+                base = sm["sims"]
+            assert np.max(np.abs(sm["sims"] - base)) <= 1e-7 * scale
+    finally:
+        ctx.set_option("lookahead", 1); ctx.set_option("outer_single", 0)
     P.close()
