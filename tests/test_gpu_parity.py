@@ -419,3 +419,38 @@ def test_simulate_predict_independent_of_schedule(ctx):
     finally:
         ctx.set_option("lookahead", 1); ctx.set_option("outer_single", 0)
     P.close()
+
+
+def test_nll_loocv_independent_of_schedule(ctx):
+    """The likelihood (single and batched), preMats and LOOCV on a ragged size under every scheduling option: outer panel
+    widths 1/2/3/5/16 of the batched path, 1/2/4/8/16/by-size of the look-ahead path, look-ahead off, 1 or 8 streams."""
+    n = 1333
+    case = make_case(41, n, 3, [30, 20], [4, 3], ["B-splines", "PCA"], ["L2_bygroup", "L2_byindex"])
+    Ms = oracle_dists(case)
+    theta = theta_frac(Ms, 0.3)
+    ker, nug = "matern5_2", 1e-8
+    r_nll, r_s2 = ref.negLogLik(theta, [], Ms, case["y"], ker, nug)
+    L_ref, z_ref = ref.preMats(Ms, case["y"], r_s2, theta, ker, nug)
+    yp_ref = ref.getOut_loocv(L_ref, r_s2, nug, case["y"])
+    P = _problem(ctx, case)
+    th3 = np.stack([theta, 1.1 * theta, theta], axis=1)
+    tol = _nll_tol(r_nll, n)
+    try:
+        for la, outer_single, outer, streams in ((1, 0, 16, 8), (1, 1, 16, 8), (1, 2, 1, 1), (1, 4, 2, 8), (1, 8, 3, 2),
+                                                 (1, 16, 5, 8), (0, 0, 16, 1), (0, 0, 1, 8), (0, 0, 3, 3)):
+            for name, val in (("lookahead", la), ("outer_single", outer_single), ("outer", outer), ("streams", streams)):
+                ctx.set_option(name, val)
+            nll1, s1, i1 = P.nll_batch(ker, nug, theta)
+            nll3, s3, i3 = P.nll_batch(ker, nug, th3)
+            assert i1[0] == 0 and (i3 == 0).all()
+            assert abs(nll1[0] - r_nll) <= tol and abs(nll3[0] - r_nll) <= tol and nll3[0] == nll3[2]
+            assert abs(s1[0] - r_s2) <= 1e-8 * r_s2
+            L, z = P.premats(ker, nug, r_s2, theta)
+            assert np.max(np.abs(L - L_ref)) <= 1e-9 * np.max(np.abs(L_ref))
+            assert np.max(np.abs(z - z_ref)) <= 1e-8 * np.max(np.abs(z_ref))
+            yp, q2 = P.loocv()
+            assert np.max(np.abs(yp - yp_ref)) <= 1e-7 * max(1.0, np.max(np.abs(yp_ref))), (la, outer_single, outer)
+    finally:
+        for name, val in (("lookahead", 1), ("outer_single", 0), ("outer", 16), ("streams", 8)):
+            ctx.set_option(name, val)
+    P.close()
