@@ -9,9 +9,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fungp_b200  # noqa: E402
-from helpers import make_case  # noqa: E402
+from fungp_b200 import synth  # noqa: E402
 
 out = {}
 ctx = fungp_b200.Context(1)
@@ -24,8 +23,9 @@ def run(n, B, streams, lookahead, ker="gauss", reps=3, profile=False, outer=4):
     ctx.set_option("streams", streams)
     ctx.set_option("lookahead", lookahead)
     ctx.set_option("profile", 1 if profile else 0)
-    case = make_case(n, n, 4, [100, 100], [5, 5], ["B-splines"] * 2, ["L2_bygroup"] * 2)
-    P = fungp_b200.Problem(ctx, case["sIn"], case["coefs"], case["J"], case["dis"], case["y"])
+    sIn, fIn, y = synth.make_data(n, n, 4, [100, 100])
+    proj = [ctx.project(f, 5, "B-splines") for f in fIn]
+    P = fungp_b200.Problem(ctx, sIn, [c for (_, _, c) in proj], [j for (_, j, _) in proj], ["L2_bygroup"] * 2, y)
     theta = 0.25 * 2.0 * P.dist_max()
     th = np.repeat(theta[:, None], B, axis=1) * (1.0 + 0.01 * np.arange(B))[None, :]
     P.nll_batch(ker, 1e-8, th)  # warm

@@ -2,7 +2,7 @@
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import fungp_b200
 from fungp_b200 import synth
 ctx = fungp_b200.Context(1)
