@@ -133,70 +133,121 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
     }
     __syncthreads();
 
+    // Pipelined over the four sub-steps: the chain of sub-step s runs on the two warps that own its rows (2s, 2s+1)
+    // WHILE the other six warps are still in the rank-32 update of sub-step s-1 -- those two warps have a single
+    // update task each (the 16 x 32 halves of the next diagonal block), do it first, meet at a 64-thread barrier and
+    // start the chain.  The inverse warp keeps E_ss in registers until the update has finished reading XP.
+    double e[SB];                         // E_ss row of the inverse warp, written out after barrier C
     for (int s = 0; s < NB / SB; ++s) {
         const int o = s * SB;
         PROF(1 + 3 * s);
-        // ================= (a) 32x32 Cholesky (warp 0) and its inverse transpose (warp 1, one column behind) ========
-        if (warp == 0) {
-            // No branch, barrier or fence inside the 32 steps: shared memory is touched through volatile asm only, so
-            // that ptxas is free to interleave the trailing updates of step j-1 with the pivot chain of step j.
-            double a[SB];
+        // ================= (c) rank-32 update with the panel of sub-step s-1, DMMA =================
+        if (s > 0) {
+            const int c_first = o;                                    // columns right of sub-block s-1
+            const int nnb = (NB - c_first) / 8;                       // 8-column blocks to the right: 12, 8, 4
+            const int rbase = warp * 16;
+            double af[2][8];
 #pragma unroll
-            for (int j = 0; j < SB; ++j) a[j] = T[(o + j) * LDT + o + lane];
-            double dg = T[(o + lane) * LDT + o + lane];
-            int firstBad = 0;
-            const uint32_t tS = (uint32_t)__cvta_generic_to_shared(T + o * LDT + o);   // sub-block origin
-            const uint32_t rS = (uint32_t)__cvta_generic_to_shared(rinvS);
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                double d = __shfl_sync(0xffffffffu, dg, j);
-                const bool bad = !(d > 0.0);   // not positive definite: remember the minor's order, keep going finite
-                firstBad = (bad && firstBad == 0) ? j + 1 : firstBad;
-                d = bad ? 1.0 : d;
-                const double rinv = pivot_rsqrt(d);
-                double l = a[j] * rinv;
-                l = lane > j ? l : (lane == j ? d * rinv : 0.0);
-                dg = fma(-l, l, dg);
-                if (lane >= j) sts_f64(tS + (uint32_t)((j * LDT + lane) * 8), l);
-                if (lane == 0) sts_f64(rS + j * 8, rinv);
-                if (j + 1 < SB) {
-                    const double ln = __shfl_sync(0xffffffffu, l, j + 1);
-                    a[j + 1] = fma(-l, ln, a[j + 1]);
+                for (int k4 = 0; k4 < 8; ++k4) af[mi][k4] = XP[(k4 * 4 + fk) * XLD + rbase + mi * 8 + fr];
+            for (int nb0 = 0; nb0 < nnb; nb0 += 4) {
+                // 16 rows x 32 columns at a time; skip when every entry is in the not-yet-started E region
+                const int cb = c_first + nb0 * 8;
+                if (rbase + 15 < cb && rbase >= c_first) continue;
+                double acc[2][4][2];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    double bf[4];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) bf[ni] = XP[(k4 * 4 + fk) * XLD + cb + ni * 8 + fr];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][k4], bf[ni]);
                 }
-                // column j and 1/l_jj are in shared memory: every lane releases its own stores to warp 1
-                mbar_arrive(barAddr + 8 * j);
-                // column j read back as 16-byte pairs (shared-memory loads are the scarce resource here)
-                if (((j + 2) & 1) && j + 2 < SB) a[j + 2] = fma(-l, lds_f64(tS + (uint32_t)((j * LDT + j + 2) * 8)), a[j + 2]);
 #pragma unroll
-                for (int c = (j + 3) & ~1; c + 1 < SB; c += 2) {
-                    const double2 lc = lds_v2f64(tS + (uint32_t)((j * LDT + c) * 8));
-                    a[c] = fma(-l, lc.x, a[c]);
-                    a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int r = rbase + mi * 8 + fr, c = cb + ni * 8 + 2 * fk + h;
+                            if (r >= c || r < c_first) T[c * LDT + r] -= acc[mi][ni][h];
+                        }
+            }
+        }
+        // ================= (a) 32x32 Cholesky (warp 2s) and its inverse transpose (warp 2s+1, one column behind) =====
+        if ((warp >> 1) == s) {
+            // both halves of the diagonal sub-block have their update (each of the two warps did one half)
+            if (s > 0) asm volatile("bar.sync 1, 64;\n" ::: "memory");
+            if ((warp & 1) == 0) {
+                // No branch, barrier or fence inside the 32 steps: shared memory is touched through volatile asm only,
+                // so that ptxas is free to interleave the trailing updates of step j-1 with the pivot chain of step j.
+                double a[SB];
+#pragma unroll
+                for (int j = 0; j < SB; ++j) a[j] = T[(o + j) * LDT + o + lane];
+                double dg = T[(o + lane) * LDT + o + lane];
+                int firstBad = 0;
+                const uint32_t tS = (uint32_t)__cvta_generic_to_shared(T + o * LDT + o);   // sub-block origin
+                const uint32_t rS = (uint32_t)__cvta_generic_to_shared(rinvS);
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    double d = __shfl_sync(0xffffffffu, dg, j);
+                    const bool bad = !(d > 0.0);   // not positive definite: remember the minor's order, keep going finite
+                    firstBad = (bad && firstBad == 0) ? j + 1 : firstBad;
+                    d = bad ? 1.0 : d;
+                    const double rinv = pivot_rsqrt(d);
+                    double l = a[j] * rinv;
+                    l = lane > j ? l : (lane == j ? d * rinv : 0.0);
+                    dg = fma(-l, l, dg);
+                    if (lane >= j) sts_f64(tS + (uint32_t)((j * LDT + lane) * 8), l);
+                    if (lane == 0) sts_f64(rS + j * 8, rinv);
+                    if (j + 1 < SB) {
+                        const double ln = __shfl_sync(0xffffffffu, l, j + 1);
+                        a[j + 1] = fma(-l, ln, a[j + 1]);
+                    }
+                    // column j and 1/l_jj are in shared memory: every lane releases its own stores to the inverse warp
+                    mbar_arrive(barAddr + 8 * j);
+                    // column j read back as 16-byte pairs (shared-memory loads are the scarce resource here)
+                    if (((j + 2) & 1) && j + 2 < SB) a[j + 2] = fma(-l, lds_f64(tS + (uint32_t)((j * LDT + j + 2) * 8)), a[j + 2]);
+#pragma unroll
+                    for (int c = (j + 3) & ~1; c + 1 < SB; c += 2) {
+                        const double2 lc = lds_v2f64(tS + (uint32_t)((j * LDT + c) * 8));
+                        a[c] = fma(-l, lc.x, a[c]);
+                        a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                    }
+                }
+                if (firstBad && lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + firstBad;
+            } else {
+                // E_ss = L_ss^-T, lane = row of E, with the columns the chain warp has released
+#pragma unroll
+                for (int j = 0; j < SB; ++j) e[j] = (j == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int j = 0; j < SB; ++j) {
+                    for (int spin = 0; !mbar_try_wait(barAddr + 8 * j, s & 1); ++spin)
+                        if (spin > (1 << 24)) __trap();   // a protocol bug must trap, never hang the device
+                    const double x = e[j] * rinvS[j];     // E(lane, j); zero for lane > j
+                    e[j] = x;
+                    if ((j + 1) & 1) {
+                        const double lc = T[(o + j) * LDT + o + j + 1];
+                        if (j + 1 < SB) e[j + 1] = fma(-x, lc, e[j + 1]);
+                    }
+#pragma unroll
+                    for (int c = (j + 2) & ~1; c + 1 < SB; c += 2) {
+                        const double2 lc = *reinterpret_cast<const double2*>(&T[(o + j) * LDT + o + c]);
+                        e[c] = fma(-x, lc.x, e[c]);
+                        e[c + 1] = fma(-x, lc.y, e[c + 1]);
+                    }
                 }
             }
-            if (firstBad && lane == 0 && info && *(info + blockIdx.x) == 0) *(info + blockIdx.x) = infoOff + o + firstBad;
-        } else if (warp == 1) {
-            // E_ss = L_ss^-T, lane = row of E: E(:, c) -= E(:, j) L(c, j) / ... with the columns warp 0 has released
-            double e[SB];
-#pragma unroll
-            for (int j = 0; j < SB; ++j) e[j] = (j == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                for (int spin = 0; !mbar_try_wait(barAddr + 8 * j, s & 1); ++spin)
-                    if (spin > (1 << 24)) __trap();   // a protocol bug must trap, never hang the device
-                const double x = e[j] * rinvS[j];     // E(lane, j); zero for lane > j
-                e[j] = x;
-                if ((j + 1) & 1) {
-                    const double lc = T[(o + j) * LDT + o + j + 1];
-                    if (j + 1 < SB) e[j + 1] = fma(-x, lc, e[j + 1]);
-                }
-#pragma unroll
-                for (int c = (j + 2) & ~1; c + 1 < SB; c += 2) {
-                    const double2 lc = *reinterpret_cast<const double2*>(&T[(o + j) * LDT + o + c]);
-                    e[c] = fma(-x, lc.x, e[c]);
-                    e[c + 1] = fma(-x, lc.y, e[c + 1]);
-                }
-            }
+        }
+        __syncthreads();     // C: update s-1 and chain s are done; XP and Eop are free
+        if (warp == 2 * s + 1) {
             // E_ss: strict upper part into T, diagonal into dinvE, operand copies for (b) and (c)
 #pragma unroll
             for (int j = 0; j < SB; ++j) {
@@ -207,7 +258,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
                 if (j == lane) dinvE[o + lane] = v;
             }
         }
-        __syncthreads();
+        __syncthreads();     // A
         PROF(2 + 3 * s);
         // ================= (b) X = B * E_ss for the rows outside the diagonal sub-block, DMMA =================
         {
@@ -247,49 +298,8 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
                         }
             }
         }
-        __syncthreads();
+        __syncthreads();     // B
         PROF(3 + 3 * s);
-        // ================= (c) rank-32 update of the columns to the right, DMMA =================
-        const int c_first = o + SB;
-        const int nnb = (NB - c_first) / 8;                       // 8-column blocks to the right: 12, 8, 4, 0
-        if (nnb > 0) {
-            const int rbase = warp * 16;
-            double af[2][8];
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) af[mi][k4] = XP[(k4 * 4 + fk) * XLD + rbase + mi * 8 + fr];
-            for (int nb0 = 0; nb0 < nnb; nb0 += 4) {
-                // 16 rows x 32 columns at a time; skip when every entry is in the not-yet-started E region
-                const int cb = c_first + nb0 * 8;
-                if (rbase + 15 < cb && rbase >= c_first) continue;
-                double acc[2][4][2];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-#pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    double bf[4];
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) bf[ni] = XP[(k4 * 4 + fk) * XLD + cb + ni * 8 + fr];
-#pragma unroll
-                    for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi][k4], bf[ni]);
-                }
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int r = rbase + mi * 8 + fr, c = cb + ni * 8 + 2 * fk + h;
-                            if (r >= c || r < c_first) T[c * LDT + r] -= acc[mi][ni][h];
-                        }
-            }
-        }
-        __syncthreads();
     }
 
     PROF(13);

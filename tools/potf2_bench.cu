@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
     printf("batch %d: %.2f us  (%s)\n", batch, best * 1e3, cudaGetErrorString(cudaGetLastError()));
     printf("load %lld\n", p[1] - p[0]);
     for (int s = 0; s < 4; ++s)
-        printf("s=%d: (a) %lld  (b) %lld  (c) %lld cycles\n", s, p[2 + 3 * s] - p[1 + 3 * s], p[3 + 3 * s] - p[2 + 3 * s],
+        printf("s=%d: (c of s-1 | a) %lld  (b) %lld  cycles  [%lld]\n", s, p[2 + 3 * s] - p[1 + 3 * s], p[3 + 3 * s] - p[2 + 3 * s],
                (s < 3 ? p[4 + 3 * s] : p[13]) - p[3 + 3 * s]);
     printf("store L %lld  store W %lld  total %lld cycles\n", p[14] - p[13], p[15] - p[14], p[15] - p[0]);
     std::vector<double> o(h.size());
