@@ -11,6 +11,7 @@
 #include "lbfgsb.hpp"
 #include "../../include/fungp_b200.h"
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <thread>
@@ -256,7 +257,11 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
         int visible = 1;
         if (cudaGetDeviceCount(&visible) != cudaSuccess) { cudaGetLastError(); visible = 1; }
         const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
-        blocking = ((unsigned)(wpd * std::max(visible, nd)) * 4u > cores * 3u) ? 2 : 0;
+        // under torchrun LOCAL_WORLD_SIZE says how many such processes share the host (the GPUs may be hidden per rank)
+        int peers = 0;
+        if (const char* lws = getenv("LOCAL_WORLD_SIZE")) peers = atoi(lws);
+        const int gpus = peers > 0 ? peers * nd : std::max(visible, nd);
+        blocking = ((unsigned)(wpd * gpus) * 4u > cores * 3u) ? 2 : 0;
     }
     // worker contexts persist in the parent context (slot = device index * 16 + worker)
     {
