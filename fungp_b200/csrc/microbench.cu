@@ -52,7 +52,10 @@ int fgp_peaks_device(double* dmma_tflops, double* dfma_tflops, double* copy_gbs)
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float ms = 0.f;
-    const int grid = nsm * 4;
+    // two CTAs of 8 warps per SM, as tools/dmma_sustained.cu: one warp per sub-partition already saturates the FP64
+    // datapath (r01_dmma_sweep.log); four CTAs per SM only add power -- on a hot board the loop then came out at 29.7
+    // instead of 37.1 TFLOP/s (power-capped clocks) while the real kernels, at 650-720 W, were unaffected
+    const int grid = nsm * 2;
     {
         const int iters = 4096;
         dmma_peak_kernel<<<grid, 256>>>(dout, 64);   // warm-up
