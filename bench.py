@@ -374,6 +374,12 @@ def run_reference(args):
         return
     import scipy.linalg as sla
     from oracle import fungp_ref as ref
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is to use every host thread it can
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     sIn, fIn, y = build_inputs()
     bcj = ref.dimReduction(fIn, CFG["pdims"], [CFG["basis"]] * len(fIn))
     J, coefs = bcj["J"], bcj["coefs"]
