@@ -165,6 +165,7 @@ def run_ours(args):
     ctx.set_option("streams", args.streams)
     ctx.set_option("outer", args.outer)
     ctx.set_option("fit_blocking", args.fit_blocking)
+    ctx.set_option("graphs", args.graphs)
     if args.fit_workers > 0:
         ctx.set_option("fit_workers", args.fit_workers)
     sIn, fIn, y = build_inputs()
@@ -439,6 +440,7 @@ def main():
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--outer", type=int, default=16)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--graphs", type=int, default=0, help="replay small-n likelihood calls as CUDA graphs in the factory fits (0/1)")
     ap.add_argument("--fit-workers", type=int, default=0, help="fit_batch worker contexts per GPU (0 = library default, 8)")
     ap.add_argument("--fit-blocking", type=int, default=-1, help="fit_batch workers: 1 sleep / 0 spin in host waits, -1 auto")
     ap.add_argument("--factory-cands", type=int, default=48, help="candidate structures per GPU for the factory metric (0 = skip)")

@@ -132,6 +132,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "lookahead")) ctx->lookahead = value != 0;
     else if (!strcmp(name, "fit_blocking")) ctx->fit_blocking = value < 0 ? -1 : std::min((int)value, 2);
     else if (!strcmp(name, "blocking_sync")) ctx->blockingSync = std::max(0, std::min((int)value, 2));
+    else if (!strcmp(name, "graphs")) ctx->graphs = value != 0;
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(0, std::min((int)value, 16));
@@ -356,6 +357,7 @@ extern "C" void fgp_problem_destroy(fgp_problem* P) {
         if (pd.y) d.pool.put(pd.y);
         if (pd.Lfac) d.pool.put(pd.Lfac);
         if (pd.Wall) d.pool.put(pd.Wall);
+        for (auto& gph : pd.graphs) if (gph.exec) cudaGraphExecDestroy(gph.exec);
     }
     delete P;
 }
@@ -526,9 +528,10 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
         if (n < 2048) ns = 1;
         else if (n < 4096) ns = std::min(ns, 2);
         const int per = cdiv(cb, ns);
-        for (int s = 0; s < ns; ++s) {
+        // one group = one launch sequence on its stream
+        auto enqueue_group = [&](int s) -> int {
             const int g0 = s * per, g1 = std::min(cb, g0 + per);
-            if (g1 <= g0) continue;
+            if (g1 <= g0) return 0;
             const int gb = g1 - g0;
             cudaStream_t st = d.sPanel[s];
             double* Mg = (double*)d.work.p + (size_t)g0 * ld * n;
@@ -550,18 +553,65 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             t.info = dInfo + g0;
             if (prof) d.timers.begin(st);
             cudaEvent_t fa = prof ? d.timers.cur : nullptr;
-            rc = trap_factor(ctx, slot, t, st, d.sBulk, ctx->lookahead && ns == 1 && gb == 1);
-            if (rc) return rc;
+            const int rcf = trap_factor(ctx, slot, t, st, d.sBulk, ctx->lookahead && ns == 1 && gb == 1);
+            if (rcf) return rcf;
             if (prof) { d.timers.cur = fa; d.timers.end(st, FgpTimers::FACTOR, 0.0); }
             launch_nll_reduce(Mg, ld, (long)ld * n, gb, n, n, var_known ? dVar : nullptr, dInfo + g0, dNll + g0, dSig + g0, st);
+            return 0;
+        };
+        // Small matrices, option "graphs": the whole call (copy in, ~26 launches, copy out) is captured the second time
+        // the same shape is seen on this problem and replayed from then on: one launch per call instead of ~30 driver
+        // calls -- what the host threads of an 8-GPU candidate search spend most of their time in.
+        NllGraph* gr = nullptr;
+        bool replayed = false;
+        if (ctx->graphs && ns == 1 && cb > 1 && !prof && !var_known && c0 == 0 && cb == B && n < 2048) {
+            ProblemDev& pdw = P->pd[slot];
+            for (auto& g : pdw.graphs)
+                if (g.ker == ker && g.B == cb && g.nugget == nugget && g.work == d.work.p && g.wbuf == d.wbuf.p &&
+                    g.small == d.small.p && g.pinned == d.pinned && g.outer == ctx->outer) { gr = &g; break; }
+            if (!gr) {
+                if (pdw.graphs.size() < 8) {
+                    NllGraph g; g.ker = ker; g.B = cb; g.nugget = nugget; g.work = d.work.p; g.wbuf = d.wbuf.p;
+                    g.small = d.small.p; g.pinned = d.pinned; g.outer = ctx->outer;
+                    pdw.graphs.push_back(g);          // first sighting: run normally (also warms the launchers' statics)
+                }
+            } else {
+                cudaStream_t st = d.sPanel[0];
+                if (!gr->exec) {
+                    cudaGraph_t graph = nullptr;
+                    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    const int rce = enqueue_group(0);
+                    cudaError_t ec = cudaMemcpyAsync(hRes, dNll, resBytes, cudaMemcpyDeviceToHost, st);
+                    cudaError_t ee = cudaStreamEndCapture(st, &graph);
+                    if (rce || ec != cudaSuccess || ee != cudaSuccess || !graph) {
+                        if (graph) cudaGraphDestroy(graph);
+                        cudaGetLastError();
+                        gr->B = -1;                   // never try this entry again; fall through to the normal path
+                        gr = nullptr;
+                    } else {
+                        cudaError_t ei = cudaGraphInstantiate(&gr->exec, graph, 0);
+                        cudaGraphDestroy(graph);
+                        if (ei != cudaSuccess) { cudaGetLastError(); gr->exec = nullptr; gr->B = -1; gr = nullptr; }
+                    }
+                }
+                if (gr && gr->exec) {
+                    CK(cudaGraphLaunch(gr->exec, st));
+                    replayed = true;
+                }
+            }
         }
+        if (!replayed)
+            for (int s = 0; s < ns; ++s) {
+                rc = enqueue_group(s);
+                if (rc) return rc;
+            }
         // join the groups on stream 0, fetch nll | sig2 | info with one copy, and wait once
         for (int s = 1; s < ns; ++s) {
             if (!d.evJoin[s]) CK(cudaEventCreateWithFlags(&d.evJoin[s], cudaEventDisableTiming));
             CK(cudaEventRecord(d.evJoin[s], d.sPanel[s]));
             CK(cudaStreamWaitEvent(d.sPanel[0], d.evJoin[s], 0));
         }
-        CK(cudaMemcpyAsync(hRes, dNll, resBytes, cudaMemcpyDeviceToHost, d.sPanel[0]));
+        if (!replayed) CK(cudaMemcpyAsync(hRes, dNll, resBytes, cudaMemcpyDeviceToHost, d.sPanel[0]));
         CK(wait_stream(ctx, d, d.sPanel[0]));
         CK(cudaGetLastError());
         memcpy(nll + b0 + c0, hRes, sizeof(double) * cb);

@@ -102,6 +102,7 @@ struct fgp_ctx {
     int lookahead = 1;
     int streams = 8;
     int fit_workers = 8;      // fgp_fit_batch: concurrent candidate fits per GPU
+    int graphs = 0;           // option "graphs": replay small-n likelihood calls as CUDA graphs (second call onwards)
     int blockingSync = 0;     // host waits sleep instead of spinning (set on fit_batch worker contexts)
     int fit_blocking = -1;    // option "fit_blocking": worker contexts of fgp_fit_batch use blocking waits (-1 = auto)
     int outer = 16;           // column tiles per outer panel for batches (trailing update K = outer*128)
@@ -113,6 +114,15 @@ struct fgp_ctx {
     std::vector<fgp_ctx*> fitWorkers;
 };
 
+// a captured launch sequence of one batched likelihood call (small n: one stream, ~26 launches), see nll_range
+struct NllGraph {
+    int ker = 0, B = 0;
+    double nugget = 0;
+    const void* work = nullptr; const void* wbuf = nullptr; const void* small = nullptr; const void* pinned = nullptr;
+    int outer = 0;
+    cudaGraphExec_t exec = nullptr;     // null: seen once, not captured yet
+};
+
 struct ProblemDev {
     bool ready = false;
     double* X = nullptr;      // n x ncoord coordinate matrix (column-major, ld = n)
@@ -122,6 +132,7 @@ struct ProblemDev {
     double* Lfac = nullptr;   // trapezoid with the factor of sig2 (R + nugget I) and the (L^-1 y)' row
     long ldL = 0;
     double* Wall = nullptr;   // inverse diagonal blocks of Lfac
+    std::vector<NllGraph> graphs;
 };
 
 struct fgp_problem {

@@ -154,7 +154,9 @@ int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
  * path of a single factorisation; 0 = chosen by size: 2 below n = 12288, 8 below 24576, else 16), "fit_workers" (1..16),
  * "fit_blocking" (host waits of the fgp_fit_batch worker contexts: 0 spin, 1 sleep on a blocking event, 2 poll and yield;
  * default -1 = yield when workers x visible GPUs exceed 3/4 of the host cores, else spin),
- * "blocking_sync" (0/1/2, default 0: the same for this context's own calls). */
+ * "blocking_sync" (0/1/2, default 0: the same for this context's own calls),
+ * "graphs" (0/1, default 0: batched likelihood calls at n < 2048 are captured as a CUDA graph the second time a shape is
+ * seen on a problem and replayed afterwards -- one driver call per evaluation batch instead of ~30). */
 int fgp_set_option(fgp_ctx* ctx, const char* name, double value);
 /* measured FP64 peaks on device 0 for the roofline denominators: register-resident DMMA (m8n8k4) loop and
  * DFMA loop, TFLOP/s; and a device copy, GB/s. */

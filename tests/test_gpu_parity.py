@@ -454,3 +454,31 @@ def test_nll_loocv_independent_of_schedule(ctx):
         for name, val in (("lookahead", 1), ("outer_single", 0), ("outer", 16), ("streams", 8)):
             ctx.set_option(name, val)
     P.close()
+
+
+def test_graph_replay_matches_direct_launches(ctx):
+    """Option "graphs": the captured launch sequence of a small-n batched likelihood gives bit-identical results to the
+    direct launches, for changing length-scales, after a not-positive-definite point, and for two batch shapes."""
+    n = 700
+    case = make_case(51, n, 2, [30], [4], ["B-splines"], ["L2_bygroup"])
+    P = _problem(ctx, case)
+    ub = 2.0 * P.dist_max()
+    rng = np.random.default_rng(5)
+    ker = "matern5_2"
+    batches = [ub[:, None] * rng.uniform(0.05, 0.9, size=(P.d, B)) for B in (7, 7, 7, 20, 7, 20)]
+    try:
+        ctx.set_option("graphs", 0)
+        want = [P.nll_batch(ker, 1e-8, th) for th in batches]
+        bad_w = P.nll_batch(ker, -1e-3, batches[0])
+        ctx.set_option("graphs", 1)
+        got = [P.nll_batch(ker, 1e-8, th) for th in batches]          # 1st sighting direct, 2nd captured, then replayed
+        bad_g = [P.nll_batch(ker, -1e-3, batches[0]) for _ in range(3)]
+        again = P.nll_batch(ker, 1e-8, batches[2])
+    finally:
+        ctx.set_option("graphs", 0)
+    for (a, b) in zip(want, got):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for bg in bad_g:
+        assert np.array_equal(bad_w[2], bg[2]) and (bg[2] > 0).any()
+    assert np.array_equal(again[0], want[2][0]) and (again[2] == 0).all()
+    P.close()

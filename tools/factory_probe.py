@@ -11,14 +11,15 @@ ctx = fungp_b200.Context(1)
 sIn, fIn, y = synth.make_data(1024, 1024, 5, [10, 22, 50])
 ants = bench.factory_candidates(96)
 base = None
-for w, blk in ((8, 2), (8, 0), (8, 2), (8, 1), (16, 2)):
+for w, blk, gph in ((8, 0, 0), (8, 0, 1), (8, 0, 0), (8, 0, 1), (8, 2, 1)):
+    ctx.set_option("graphs", gph)
     ctx.set_option("fit_blocking", blk)
     ctx.set_option("fit_workers", w)
     t0 = time.perf_counter()
     r = F.score_candidates(ctx, sIn, fIn, y, ants, NumpyRng(1))
     dt = time.perf_counter() - t0
     bad = np.nonzero(r["info"])[0]
-    print(f"workers {w} blocking {blk}: {len(ants)/dt:.1f} cand/s; failures {[(int(i), int(r['info'][i])) for i in bad]}", flush=True)
+    print(f"workers {w} blocking {blk} graphs {gph}: {len(ants)/dt:.1f} cand/s; failures {[(int(i), int(r['info'][i])) for i in bad]}", flush=True)
     if base is None:
         base = r
     else:
