@@ -96,7 +96,7 @@ class ClockSampler:
                     samples=len(sm), power_w_max=float(max(pw)))
 
 
-FACTORY = dict(n=1024, ds=5, f_lens=[10, 22, 50], seed=1024, n_starts=1, n_presample=20, nugget=1e-8)
+FACTORY = dict(n=1024, ds=5, f_lens=[10, 22, 50], seed=1024, n_starts=1, n_presample=20, nugget=1e-8, n_cand=2000, list_seed=7)
 
 
 def factory_candidates(n_cand, seed=7):
@@ -119,25 +119,74 @@ def factory_candidates(n_cand, seed=7):
     return np.stack(ants)
 
 
-def run_factory(ctx, rank, world, cands_per_gpu, barrier):
-    """fgpm_factory candidate scoring (second headline metric): n = 1024, candidates sharded over the ranks."""
-    from fungp_b200 import synth, factory as F
-    from fungp_b200.model import NumpyRng
+def factory_draws(ants, seed=11):
+    """The presample uniforms of every candidate of the fixed list, drawn in list order from ONE stream (as the sequential
+    reference loop would consume R's runif): a candidate's draws do not depend on how the list is sharded."""
+    from fungp_b200 import factory as F
+    rng = np.random.default_rng(seed)
+    ds, df, lens = FACTORY["ds"], len(FACTORY["f_lens"]), FACTORY["f_lens"]
+    npre = max(FACTORY["n_presample"], FACTORY["n_starts"])
+    return [rng.uniform(size=F.n_lengthscales(a, ds, df, lens) * npre) for a in ants]
+
+
+def run_factory(ctx, rank, world, n_cand, barrier):
+    """fgpm_factory candidate scoring (second headline metric), BASELINE.json configs[3]: n = 1024, a FIXED list of n_cand
+    structures sharded over the ranks (strong scaling: the list does not grow with the number of GPUs)."""
+    from fungp_b200 import synth
     sIn, fIn, y = synth.make_data(FACTORY["seed"], FACTORY["n"], FACTORY["ds"], FACTORY["f_lens"])
-    ants = factory_candidates(cands_per_gpu * world)
-    mine = ants[rank::world]            # round-robin deal: candidate costs vary with the structure, this evens them out
-    F.score_candidates(ctx, sIn, fIn, y, mine[:8], NumpyRng(0), nugget=FACTORY["nugget"])       # warm-up (one per worker)
-    # three repetitions of the same generation; the median is reported (host scheduling noise on shared boxes moves a
-    # 2-second measurement by +-20 %), all three are listed
-    times = []
-    for rep in range(3):
-        barrier()
-        t0 = time.perf_counter()
-        res = F.score_candidates(ctx, sIn, fIn, y, mine, NumpyRng(rank + 1), nugget=FACTORY["nugget"],
-                                 n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"])
-        barrier()
-        times.append(time.perf_counter() - t0)
-    return times, len(ants), int((res["info"] == 0).sum()), float(np.nanmax(res["fitness"]))
+    ants = factory_candidates(n_cand, FACTORY["list_seed"])
+    u01 = factory_draws(ants)
+    idx = np.arange(rank, n_cand, world)        # round-robin deal: candidate costs vary with the structure, this evens them out
+    kw = dict(nugget=FACTORY["nugget"], n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"])
+    warm = idx[:32]
+    ctx.fit_batch(sIn, fIn, y, ants[warm], [u01[i] for i in warm], **kw)       # warm-up: workspaces, streams, projections
+    w0 = [ctx.work_count(i) for i in range(4)]
+    l0 = ctx.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    res = ctx.fit_batch(sIn, fIn, y, ants[idx], [u01[i] for i in idx], **kw)
+    barrier()
+    dt = time.perf_counter() - t0
+    w1 = [ctx.work_count(i) for i in range(4)]
+    return dict(seconds=dt, n_cand=n_cand, mine=len(idx), ok=int((res["info"] == 0).sum()), best=float(np.nanmax(res["fitness"])),
+                nll_evals=w1[0] - w0[0], loocv=w1[1] - w0[1], launches=ctx.launch_count() - l0,
+                first=(int(idx[0]), float(res["fitness"][0]), float(res["nll"][0])), data=(sIn, fIn, y, ants, u01))
+
+
+def factory_cpu_baseline(data, budget_s=25.0):
+    """The oracle (numpy/scipy restatement of fgpm() + Q2loocv, oracle/) on candidates of the same fixed list, with the same
+    presample draws, on the host cores: a bounded sample (whole candidates until the time budget is spent)."""
+    from oracle import fungp_ref as ref
+    from fungp_b200 import factory as F
+    sIn, fIn, y, ants, u01 = data
+
+    class _Draws:
+        def __init__(self, u):
+            self.u = u
+
+        def runif(self, k):
+            assert k == self.u.size
+            return self.u
+
+    done, t0, fits = 0, time.perf_counter(), []
+    for c in range(len(ants)):
+        kw = F.decode_ant(ants[c], FACTORY["ds"], len(FACTORY["f_lens"]))
+        try:
+            m = ref.fgpm(sIn=sIn[:, kw["s_active"]] if kw["s_active"] else None,
+                         fIn=[fIn[j] for j in kw["f_active"]] if kw["f_active"] else None, sOut=y, kerType=kw["kerType"],
+                         f_disType=kw["f_disType"] or "L2_bygroup", f_pdims=kw["f_pdims"] or 3, f_basType=kw["f_basType"] or "B-splines",
+                         nugget=FACTORY["nugget"], n_starts=FACTORY["n_starts"], n_presample=FACTORY["n_presample"], rng=_Draws(u01[c]))
+            fits.append(float(ref.q2_loocv(m)))
+        except Exception:
+            fits.append(float("nan"))
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"the first {done} candidates of the fixed 2000-structure list, full oracle fgpm() (presample 20, scipy L-BFGS-B with "
+                      "R-style finite differences, preMats) + Q2loocv each; numpy element-wise passes single-threaded as in R, OpenBLAS all cores",
+            "seconds": dt, "q2": fits}
 
 
 def build_inputs(rank=0):
@@ -166,6 +215,7 @@ def run_ours(args):
     ctx.set_option("outer", args.outer)
     ctx.set_option("fit_blocking", args.fit_blocking)
     ctx.set_option("graphs", args.graphs)
+    ctx.set_option("fit_mode", args.fit_mode)
     if args.fit_workers > 0:
         ctx.set_option("fit_workers", args.fit_workers)
     sIn, fIn, y = build_inputs()
@@ -197,6 +247,8 @@ def run_ours(args):
         Pe = fungp_b200.Problem(ctx, sIn, coefs, J, dis, y)
         nll, s2, info = Pe.nll_batch(ker, nug, thetas)
         Pe.close()
+        if info.any() or not np.all(np.isfinite(nll)):
+            raise SystemExit(f"bench.py: factorisation failed in the end-to-end arm, info={info}")
         return nll
 
     # ---- device-resident arm
@@ -226,6 +278,15 @@ def run_ours(args):
         step_e2e()
     barrier()
     wall_e2e = time.perf_counter() - t1
+    # ---- one evaluation at a time (what optim's fn calls and every line-search step are): look-ahead path
+    single_ms = None
+    if rank == 0:
+        for _ in range(2):
+            P.nll_batch(ker, nug, thetas[:, :1])
+        ts = time.perf_counter()
+        for _ in range(5):
+            P.nll_batch(ker, nug, thetas[:, :1])
+        single_ms = (time.perf_counter() - ts) / 5 * 1e3
 
     fac = None
     if args.factory_cands > 0:
@@ -236,12 +297,37 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     wall, dev_ms, wall_e2e = [float(x) for x in tt.cpu()]
     if fac is not None:
-        ft = torch.tensor(fac[0], dtype=torch.float64)
-        fo = torch.tensor([float(fac[2])], dtype=torch.float64)
+        ft = torch.tensor([fac["seconds"]], dtype=torch.float64)
+        fo = torch.tensor([float(fac["ok"]), float(fac["nll_evals"]), float(fac["loocv"]), float(fac["launches"])], dtype=torch.float64)
+        fb = torch.tensor([fac["best"]], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ft, op=dist.ReduceOp.MAX)
             dist.all_reduce(fo, op=dist.ReduceOp.SUM)
-        fac = ([float(x) for x in ft], fac[1], int(fo.item()), fac[3])
+            dist.all_reduce(fb, op=dist.ReduceOp.MAX)
+        fac.update(seconds=float(ft.item()), ok=int(fo[0].item()), nll_evals=int(fo[1].item()), loocv=int(fo[2].item()),
+                   launches=int(fo[3].item()), best=float(fb.item()))
+    # ---- the path a single R session uses: ONE process, one context over all N GPUs (fgp_ctx_create(N)); rank 0 scores a
+    # slice of the same list through it while the other ranks wait, and checks it against its own per-rank results
+    inproc = None
+    if world > 1 and fac is not None and args.inproc_cands > 0:
+        barrier()
+        if rank == 0:
+            sInF, fInF, yF, ants, u01 = fac["data"]
+            k = min(args.inproc_cands, len(ants))
+            ctxN = fungp_b200.Context(device_ids=list(range(world)))
+            ctxN.fit_batch(sInF, fInF, yF, ants[:2 * world], u01[:2 * world], nugget=FACTORY["nugget"])
+            ti = time.perf_counter()
+            rN = ctxN.fit_batch(sInF, fInF, yF, ants[:k], u01[:k], nugget=FACTORY["nugget"], n_starts=FACTORY["n_starts"],
+                                n_presample=FACTORY["n_presample"])
+            ti = time.perf_counter() - ti
+            thN = np.tile(thetas, (1, world))
+            nllN, _, _ = fungp_b200.Problem(ctxN, sIn, coefs, J, dis, y).nll_batch(ker, nug, thN)
+            same_first = bool(rN["fitness"][0] == fac["first"][1] and rN["nll"][0] == fac["first"][2]) if fac["first"][0] == 0 else None
+            inproc = {"devices": ctxN.device_count, "candidates": int(k), "candidates_per_s": k / ti, "fitted_ok": int((rN["info"] == 0).sum()),
+                      "first_candidate_bit_identical_to_rank0": same_first,
+                      "nll_batch_sharded_bit_identical": bool(np.array_equal(nllN[:B], nll_last) and np.array_equal(nllN[:B], nllN[-B:]))}
+            ctxN.close()
+        barrier()
     total_evals = world * B * args.steps
     # the step ends with a host-synchronous read of its results, so wall time >= device time; report the wall clock
     value = total_evals / wall
@@ -251,11 +337,10 @@ def run_ours(args):
 
     out = None
     if rank == 0:
-        # ---- roofline of the dominant kernel, measured live with CUDA events around every launch (separate pass)
-        # DMMA and DFMA share one FP64 datapath on sm_100a (profiles/r01_peaks.md), so the denominator is the best of
-        # both loops over three attempts (a single attempt right after the timed region has come out 20 % low); never
-        # below this repo's own 4-second sustained measurement (37.08, tools/dmma_sustained.cu) -- a low denominator
-        # would overstate the fraction
+        # ---- FP64 denominator.  DMMA and DFMA share one FP64 datapath on sm_100a (profiles/r01_peaks.md), so it is the
+        # best of both register-resident loops over three attempts (a single attempt right after the timed region has come
+        # out 20 % low); never below this repo's own 4-second sustained measurement (37.08, tools/dmma_sustained.cu) -- a low
+        # denominator would overstate the fraction
         attempts = []
         for _ in range(3):
             attempts.append(ctx.measure_peaks())
@@ -269,6 +354,7 @@ def run_ours(args):
         fp64_peak = max(live, 37.08)
         peak_src = ("measured live: best of register-resident DMMA / DFMA loops over 3 attempts (fgp_measure_peaks)" if live >= 37.08 else
                     "this repo's sustained DMMA measurement on this pool (37.08, profiles/r01_peaks.md); the live loops gave %.2f" % live)
+        # per-launch CUDA events (profile mode: one stream, two single evaluations) -- explains the step, is not the step
         ctx.set_option("profile", 1)
         P.nll_batch(ker, nug, thetas[:, :2])
         P.nll_batch(ker, nug, thetas[:, :2])
@@ -283,15 +369,19 @@ def run_ours(args):
         except Exception:
             hbm_peak = 6650.0
         traffic, traffic_note = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = tj["update_kernel_dram_bytes_per_launch"]
-            traffic_note = ("ncu capture of the K=2048 top-level update launch: %.1f GFLOP, %.1f MB algorithmic, %.1f TFLOP/s and DMMA "
-                            "pipe %.1f %% active under ncu" % (tj["flops_per_launch"] / 1e9, tj["algorithmic_bytes_per_launch"] / 1e6,
-                                                               tj["tflops_under_ncu"], tj["dmma_pipe_active_pct"]))
-        except Exception:
-            pass
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+                traffic = tj["update_kernel_dram_bytes_per_launch"]
+                traffic_note = ("%s: ncu capture of the K=%d top-level update launch: %.1f GFLOP, %.1f MB algorithmic, %.1f TFLOP/s and "
+                                "DMMA pipe %.1f %% active under ncu" % (name, tj.get("K", 2048), tj["flops_per_launch"] / 1e9,
+                                                                        tj["algorithmic_bytes_per_launch"] / 1e6, tj["tflops_under_ncu"],
+                                                                        tj["dmma_pipe_active_pct"]))
+                break
+            except Exception:
+                pass
         chol_flops = n ** 3 / 3.0
+        step_tf = chol_flops * total_evals / wall / world / 1e12      # per GPU, whole step, everything else included in the time
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -307,31 +397,50 @@ def run_ours(args):
                     "ms_per_step": wall_e2e / args.steps * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (trailing update of the blocked Cholesky, FP64 DMMA m8n8k4)",
-                         "achieved": upd_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": upd_tf / fp64_peak,
+            # achieved = ALGORITHMIC flops of the blocked Cholesky (n^3/3 per evaluation) over the timed step itself: assembly,
+            # diagonal blocks, panel solves and reductions are all inside the time, so this can only understate the kernel
+            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (trailing update of the blocked Cholesky, FP64 DMMA m8n8k4) -- "
+                                                      "measured as the whole timed step",
+                         "achieved": step_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": step_tf / fp64_peak,
+                         "flops_per_step_per_gpu": chol_flops * B,
                          "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": peak_src + "; MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = 37.2 TFLOP/s "
                                         "at 1965 MHz",
-                         "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
-                         "launch_ms_avg": tm["update_ms"] / max(1, tm["update_launches"]),
-                         "cholesky_tflops_whole_step": chol_flops * total_evals / wall / world / 1e12,
-                         "cholesky_frac_of_peak_whole_step": chol_flops * total_evals / wall / world / 1e12 / fp64_peak},
+                         "update_kernel_profiled": {"note": "per-launch CUDA events, one stream, two single evaluations (not the batched step); "
+                                                            "flops count the triangle of diagonal tiles",
+                                                    "tflops": upd_tf, "frac": upd_tf / fp64_peak,
+                                                    "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
+                                                    "launch_ms_avg": tm["update_ms"] / max(1, tm["update_launches"])}},
+            "single_eval": {"ms": single_ms, "tflops": chol_flops / (single_ms * 1e-3) / 1e12, "frac": chol_flops / (single_ms * 1e-3) / 1e12 / fp64_peak,
+                            "note": "one fgp_nll_batch call with B = 1 (look-ahead schedule), host wall clock, mean of 5"},
             "roofline_assembly": {"bound": "hbm", "kernel": "assemble_kernel<gauss> (fused distance + correlation, lower triangle)",
                                   "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                                   "algorithmic_bytes_per_launch": asm_bytes / 2, "launch_ms": tm["assembly_ms"] / 2,
-                                  "note": "FP64-issue bound: 53.5 FP64 instructions per 8-byte entry at this structure (ncu), DMMA and DFMA share one datapath; kernel ceiling = 41 % of HBM (DESIGN.md 2.3)"},
+                                  "note": "FP64-issue bound: DMMA and DFMA share one datapath (DESIGN.md 2.3)"},
             "kernel_ms_profiled_2evals": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
             "fp64_peaks_measured": peaks,
             "nll_check": float(nll_last[0]),
         }
         if fac is not None:
-            fsec = sorted(fac[0])[len(fac[0]) // 2]      # median repetition (each already the max over ranks)
-            out["factory"] = {"metric": "fgpm_factory candidates/sec", "value": fac[1] / fsec, "unit": "candidates/s",
-                              "candidates": fac[1], "fitted_ok": fac[2], "seconds": fsec,
-                              "runs_candidates_per_s": [fac[1] / t for t in fac[0]], "n_gpus": world,
-                              "config": "BASELINE.json configs[3] sizes: n=1024, 5 scalar + 3 functional (len 10/22/50) candidate "
-                                        "structures from a fixed pre-generated list, full fit (presample 20, L-BFGS-B, preMats) + "
-                                        "Q2loocv per candidate via fgp_fit_batch; candidates sharded over ranks, no collective"}
+            nf = FACTORY["n"]
+            agg_flops = fac["nll_evals"] * nf ** 3 / 3.0 + fac["loocv"] * 2.0 * nf ** 3 / 3.0
+            agg_tf = agg_flops / fac["seconds"] / 1e12
+            out["factory"] = {"metric": "fgpm_factory candidates/sec", "value": fac["n_cand"] / fac["seconds"], "unit": "candidates/s",
+                              "candidates": fac["n_cand"], "fitted_ok": fac["ok"], "seconds": fac["seconds"], "n_gpus": world,
+                              "scaling": "strong", "best_q2": fac["best"],
+                              "likelihood_evaluations": fac["nll_evals"], "loocv_factorisations": fac["loocv"],
+                              "gpu_launches": fac["launches"],
+                              "roofline": {"bound": "tensor", "achieved": agg_tf, "peak": fp64_peak * world, "unit": "TFLOP/s",
+                                           "frac": agg_tf / (fp64_peak * world),
+                                           "note": "aggregate algorithmic FP64 flops: likelihood evaluations x n^3/3 + leave-one-out "
+                                                   "factorisations x 2 n^3/3, over the whole call (host optimiser, projections included)"},
+                              "config": "BASELINE.json configs[3]: n=1024, 5 scalar + 3 functional (len 10/22/50), the fixed pre-generated list "
+                                        "of 2000 candidate structures (seed 7) sharded round-robin over the ranks; per candidate: presample 20, "
+                                        "L-BFGS-B (lock-step over all in-flight candidates, fgp_fit_batch), Q2loocv; no collective"}
+            if inproc is not None:
+                out["factory"]["in_process_multi_gpu"] = inproc
+            if world == 1 and not args.skip_cpu:
+                out["factory"]["cpu_baseline"] = factory_cpu_baseline(fac["data"])
         if world == 1 and not args.skip_cpu:
             out["cpu_baseline"] = cpu_baseline(sIn, coefs, J, y, thetas[:, 0], nll_last[0])
     if world > 1:
@@ -443,7 +552,10 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="replay small-n likelihood calls as CUDA graphs in the factory fits (0/1)")
     ap.add_argument("--fit-workers", type=int, default=0, help="fit_batch worker contexts per GPU (0 = library default, 8)")
     ap.add_argument("--fit-blocking", type=int, default=-1, help="fit_batch workers: 1 sleep / 0 spin in host waits, -1 auto")
-    ap.add_argument("--factory-cands", type=int, default=48, help="candidate structures per GPU for the factory metric (0 = skip)")
+    ap.add_argument("--factory-cands", type=int, default=FACTORY["n_cand"],
+                    help="length of the fixed candidate list for the factory metric, sharded over the GPUs (0 = skip)")
+    ap.add_argument("--fit-mode", type=int, default=1, help="fgp_fit_batch: 1 lock-step driver (one host thread per GPU), 0 one thread per candidate")
+    ap.add_argument("--inproc-cands", type=int, default=256, help="N > 1: candidates rank 0 also scores through ONE context over all N GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

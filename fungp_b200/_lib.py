@@ -22,6 +22,7 @@ SIGNATURES = {
     "fgp_version": (C.c_char_p, []),
     "fgp_bspline_basis": (C.c_int, [C.c_int, C.c_int, c_dp]),
     "fgp_project": (C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]),
+    "fgp_test_project_host": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "fgp_problem_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dpp, c_dpp, c_dp,
                                      C.POINTER(C.c_void_p)]),
     "fgp_problem_destroy": (None, [C.c_void_p]),
@@ -45,6 +46,7 @@ SIGNATURES = {
     "fgp_get_timing": (C.c_int, [C.c_void_p, c_dp]),
     "fgp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "fgp_launch_count": (C.c_longlong, []),
+    "fgp_work_count": (C.c_longlong, [C.c_int]),
     "fgp_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "fgp_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "fgp_measure_peaks": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),

@@ -92,6 +92,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.fgp_launch_count())
 
+    def work_count(self, which):
+        """0 likelihood factorisations, 1 leave-one-out factorisations, 2 preMats factorisations, 3 candidates scored"""
+        return int(self.lib.fgp_work_count(int(which)))
+
     def mark(self, idx):
         self.check(self.lib.fgp_mark(self.h, idx), "fgp_mark")
 

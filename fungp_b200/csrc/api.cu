@@ -30,7 +30,7 @@ void fgp_set_err_cuda(fgp_ctx* ctx, const char* what, cudaError_t e, const char*
 // Host wait for a stream.  Worker contexts of fgp_fit_batch (blockingSync) sleep on an event created with
 // cudaEventBlockingSync instead of spinning: 8 workers per GPU on an 8-GPU box are 64 waiting threads, more than the
 // box has cores.  User contexts keep the lower-latency spin of cudaStreamSynchronize.
-static cudaError_t wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st) {
+cudaError_t fgp_wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st) {
     if (!ctx->blockingSync) return cudaStreamSynchronize(st);
     if (!d.evWait) {
         cudaError_t e = cudaEventCreateWithFlags(&d.evWait, cudaEventBlockingSync | cudaEventDisableTiming);
@@ -50,16 +50,13 @@ static cudaError_t wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st) {
     return cudaEventSynchronize(d.evWait);
 }
 
+static inline cudaError_t wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st) { return fgp_wait_stream(ctx, d, st); }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-static inline long roundup(long a, long b) { return (a + b - 1) / b * b; }
-// leading dimension: multiple of 16 doubles (128 B); avoid large power-of-two strides
-static inline long pick_ld(long rows) {
-    long ld = roundup(rows, 16);
-    if (ld % 512 == 0) ld += 16;
-    return ld;
-}
+static inline long roundup(long a, long b) { return fgp_roundup(a, b); }
+static inline long pick_ld(long rows) { return fgp_pick_ld(rows); }
 
 std::atomic<long long> g_fgp_launches{0};
+std::atomic<long long> g_fgp_work[4];
 
 extern "C" const char* fgp_version(void) { return "fungp_b200 0.1 (sm_100a, FP64 DMMA)"; }
 
@@ -106,6 +103,11 @@ extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
     if (!ctx) return;
     for (fgp_ctx* w : ctx->fitWorkers) fgp_ctx_destroy(w);
     ctx->fitWorkers.clear();
+    if (ctx->lockState && ctx->lockFree) {
+        if (!ctx->dev.empty()) cudaSetDevice(ctx->dev[0].device);
+        ctx->lockFree(ctx->lockState);
+        ctx->lockState = nullptr;
+    }
     for (auto& d : ctx->dev) {
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();
@@ -134,6 +136,10 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "blocking_sync")) ctx->blockingSync = std::max(0, std::min((int)value, 2));
     else if (!strcmp(name, "graphs")) ctx->graphs = value != 0;
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
+    else if (!strcmp(name, "fit_mode")) ctx->fit_mode = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "fit_points")) ctx->fit_points = std::max(0, std::min((int)value, 4096));
+    else if (!strcmp(name, "fit_lanes")) ctx->fit_lanes = std::max(0, std::min((int)value, 2));
+    else if (!strcmp(name, "predict_reserve")) ctx->predict_reserve = std::max(128, std::min((int)value, 1 << 20));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(0, std::min((int)value, 16));
     else if (!strcmp(name, "streams")) ctx->streams = std::max(1, std::min((int)value, (int)DevState::MAXSTREAMS));
@@ -159,6 +165,7 @@ extern "C" int fgp_get_timing(fgp_ctx* ctx, double* out8) {
 }
 
 extern "C" long long fgp_launch_count(void) { return g_fgp_launches.load(); }
+extern "C" long long fgp_work_count(int which) { return (which >= 0 && which < 4) ? g_fgp_work[which].load() : -1; }
 
 // device-side stopwatch over ALL of the library's streams on device 0: mark(i) records an event that follows every
 // stream's queued work; elapsed(i, j) is the CUDA-event time between two marks.
@@ -249,6 +256,20 @@ void whitening_factor(const double* J, int p, std::vector<double>& W) {
     }
 }
 
+// whitened coefficients z = c W, J = W W': ||z_i - z_j||^2 = (c_i - c_j)' J (c_i - c_j)
+// (the bilinear form of R/7_distanceFunctions.R:39-45); z must be zero-initialised
+void whiten_columns(const double* c, int m, int p, const double* W, double* zcols) {
+    for (int a = 0; a < p; ++a) {
+        double* z = zcols + (size_t)a * m;
+        for (int b = 0; b < p; ++b) {
+            const double wba = W[b + (size_t)a * p];
+            if (wba == 0.0) continue;
+            const double* cb = c + (size_t)b * m;
+            for (int r = 0; r < m; ++r) z[r] += cb[r] * wba;
+        }
+    }
+}
+
 void build_coords(const fgp_problem* P, int m, const double* sIn, const double* const* coefs, std::vector<double>& X) {
     X.assign((size_t)m * P->ncoord, 0.0);
     int col = 0;
@@ -259,18 +280,8 @@ void build_coords(const fgp_problem* P, int m, const double* sIn, const double* 
         if (P->dis[i] == FGP_DIST_BYINDEX) {
             for (int a = 0; a < p; ++a, ++col) memcpy(&X[(size_t)col * m], c + (size_t)a * m, sizeof(double) * m);
         } else {
-            // whitened coefficients z = c W, J = W W': ||z_i - z_j||^2 = (c_i - c_j)' J (c_i - c_j)
-            // (the bilinear form of R/7_distanceFunctions.R:39-45)
-            const double* W = P->Jw[i].data();
-            for (int a = 0; a < p; ++a, ++col) {
-                double* z = &X[(size_t)col * m];
-                for (int b = 0; b < p; ++b) {
-                    const double wba = W[b + (size_t)a * p];
-                    if (wba == 0.0) continue;
-                    const double* cb = c + (size_t)b * m;
-                    for (int r = 0; r < m; ++r) z[r] += cb[r] * wba;
-                }
-            }
+            whiten_columns(c, m, p, P->Jw[i].data(), &X[(size_t)col * m]);
+            col += p;
         }
     }
 }
@@ -515,6 +526,7 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
 
     for (int c0 = 0; c0 < B; c0 += chunk) {
         const int cb = std::min(chunk, B - c0);
+        FGP_COUNT_WORK(0, cb);
         for (int i = 0; i < cb; ++i) kernel_scales(ker, nt, thetas + (size_t)(b0 + c0 + i) * nt, hScale + (size_t)i * nt);
         // NOTE: every host->device copy below is issued on the stream that consumes it.  The library's streams are
         // non-blocking: they do not wait for the legacy default stream, and a cudaMemcpy from pageable memory may return
@@ -678,6 +690,7 @@ extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, 
     t.cpre = 0; t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
     int rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
     if (rc) return rc;
+    FGP_COUNT_WORK(2, 1);
     int hinfo = 0;
     CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(wait_stream(ctx, d, st));
@@ -758,8 +771,7 @@ extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const doub
     rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
     if (rc) return rc;
     // mean = LInvK' LInvY ; sd = sqrt(pmax(sig2 - colSums(LInvK^2), 0))     (R/4_prediction_SF.R:10-11)
-    launch_rowgemv(Mw, ld, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, dMean, st);
-    launch_rownorm2(Mw, ld, holeHi, m, n, 0, dNorm, st);
+    launch_rowstats(Mw, ld, 0, 1, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, 0, dNorm, dMean, st);
     std::vector<double> hn(m);
     CK(cudaMemcpyAsync(mean, dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
@@ -843,8 +855,7 @@ extern "C" int fgp_simulate(fgp_problem* P, int m, const double* sNew, const dou
     t.cpre = ncTA; t.upperRows = 0; t.W = Ww; t.strideW = 0; t.info = dInfo;
     rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
     if (rc) return rc;
-    launch_rowgemv(Mw, ld, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, dMean, st);
-    launch_rownorm2(Mw, ld, holeHi, m, n, 0, dNorm, st);
+    launch_rowstats(Mw, ld, 0, 1, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, 0, dNorm, dMean, st);
     launch_lower_times(Mw + holeHi + (size_t)holeHi * ld, ld, m, dZ, nsim, dMean, dSims, st);
     int hinfo = 0;
     std::vector<double> hn(m), hm(m);
@@ -899,9 +910,9 @@ extern "C" int fgp_loocv(fgp_problem* P, double* y_pre, double* q2) {
     t.cpre = 0; t.upperRows = 1; t.W = (double*)d.wbuf.p; t.strideW = 0; t.info = dInfo;
     int rc = trap_factor(ctx, 0, t, st, d.sBulk, false);
     if (rc) return rc;
+    FGP_COUNT_WORK(1, 1);
     // X = L^-T in the extra rows: diag(Rinv)_i = |X_i.|^2 ; (Rinv y)_i = X_i. (L^-1 y)
-    launch_rownorm2(Mw, ld, holeHi, n, n, 1, dDiag, st);
-    launch_rowgemv(Mw, ld, holeHi, n, n, 1, Mw + n, ld, dRy, st);
+    launch_rowstats(Mw, ld, 0, 1, holeHi, n, n, 1, Mw + n, ld, 0, dDiag, dRy, st);
     std::vector<double> hd(n), hr(n);
     int hinfo = 0;
     CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));

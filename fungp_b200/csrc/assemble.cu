@@ -91,6 +91,15 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
     }
     const int i0 = I * AT, j0 = J * AT;
     const double* scale = a.scale ? a.scale + (long)blockIdx.y * a.nterms : nullptr;
+    const double* XP = a.XP;
+    const double* XQ = a.XQ;
+    const FgpUnit* units = a.units;
+    int u0 = k.u0, u1 = k.u1;
+    if (a.elems) {
+        // heterogeneous batch: this element's own structure (the points of many candidate fits share one launch)
+        const AsmElem e = a.elems[blockIdx.y];
+        XP = XQ = e.X; units = e.units; scale = e.scale; u0 = 0; u1 = e.nunits;
+    }
 
     // this thread's rows (local): 2tx, 2tx+1, 32+2tx, 33+2tx ; cols: 4ty .. 4ty+3
     const int lr[4] = {2 * tx, 2 * tx + 1, 32 + 2 * tx, 33 + 2 * tx};
@@ -102,11 +111,11 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { S[i][j] = 0.0; Pr[i][j] = 1.0; D2[i][j] = 0.0; }
 
-    for (int ub = k.u0; ub < k.u1; ub += CC) {
-        const int nc = min(CC, k.u1 - ub);
+    for (int ub = u0; ub < u1; ub += CC) {
+        const int nc = min(CC, u1 - ub);
         __syncthreads();
         if (tid < nc) {
-            const FgpUnit un = a.units[ub + tid];
+            const FgpUnit un = units[ub + tid];
             sCol[tid] = un.col;
             sFlag[tid] = (un.kind ? 1 : 0) | (un.last ? 2 : 0);
             sScale[tid] = (KER == 0) ? 1.0 : scale[un.term];
@@ -116,8 +125,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
         for (int idx = tid; idx < nc * AT; idx += ATHREADS) {
             const int c = idx / AT, pnt = idx % AT;
             const long col = sCol[c];
-            sP[c][pnt] = (i0 + pnt < a.nP) ? a.XP[col * a.ldP + i0 + pnt] : 0.0;
-            sQ[c][pnt] = (j0 + pnt < a.nQ) ? a.XQ[col * a.ldQ + j0 + pnt] : 0.0;
+            sP[c][pnt] = (i0 + pnt < a.nP) ? XP[col * a.ldP + i0 + pnt] : 0.0;
+            sQ[c][pnt] = (j0 + pnt < a.nQ) ? XQ[col * a.ldQ + j0 + pnt] : 0.0;
         }
         __syncthreads();
 #pragma unroll 2

@@ -121,9 +121,12 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
         }
         return g;
     };
+    // algorithmic flops of an update launch: the triangle region counts its entries on and below the diagonal only
+    // (the kernel skips the warps above it), rectangles in full
     auto flops_of = [&](const GemmArgs& g) {
-        const double tiles = g.triT * (g.triT + 1) / 2.0 + (double)(g.rectNR + g.rectNR1) * g.rectNC;
-        return tiles * 2.0 * NBk * NBk * (double)g.K * t.batch;
+        const double triRows = (double)g.triT * NBk;
+        const double entries = triRows * (triRows + 1.0) / 2.0 + (double)(g.rectNR + g.rectNR1) * g.rectNC * NBk * NBk;
+        return entries * 2.0 * (double)g.K * t.batch;
     };
 
     int k = 0;
@@ -263,40 +266,51 @@ __global__ void nll_reduce_kernel(const double* M, long ld, long strideM, int n,
     }
 }
 
-// out[i] = sum_j M(row0+i, j)^2   (j < ncol; upper: only j >= i's tile start is non-zero but zeros are stored)
-__global__ void rownorm2_kernel(const double* M, long ld, int row0, int nrow, int ncol, int jstart_by_row, double* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrow) return;
-    double s = 0.0;
-    const int j0 = jstart_by_row ? (i / FGP_TILE) * FGP_TILE : 0;
-    for (int j = j0; j < ncol; ++j) {
-        const double v = M[(long)(row0 + i) + (long)j * ld];
-        s = fma(v, v, s);
+// Row statistics of the solved extra rows, one pass over the data:
+//   norm[b*nrow + i] = sum_j M_b(row0+i, j)^2            (sd of predict, diag(R^-1) of LOOCV)
+//   dot [b*nrow + i] = sum_j M_b(row0+i, j) z_b[j*zstride]   (predictive mean, R^-1 y)
+// Block = 32 consecutive rows (lanes: coalesced along the column-major rows) x 32 warps that interleave the columns;
+// the 32 partial sums of a row are added in a fixed order, so results do not depend on the launch shape.
+// jstart_by_row (LOOCV, rows of L^-T): columns left of the row's own 128-tile are known zeros and skipped.
+__global__ void __launch_bounds__(1024) rowstats_kernel(const double* M, long ld, long strideM, int row0, int nrow, int ncol,
+                                                        int jstart_by_row, const double* z, long zstride, long zbatch,
+                                                        double* norm, double* dot) {
+    __shared__ double redN[32][33], redD[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const double* Mb = M + (long)blockIdx.y * strideM;
+    const double* zb = z ? z + (long)blockIdx.y * zbatch : nullptr;
+    const int j0 = jstart_by_row ? ((blockIdx.x * 32) / FGP_TILE) * FGP_TILE : 0;
+    double sn = 0.0, sd = 0.0;
+    if (i < nrow) {
+        const double* rowp = Mb + (long)(row0 + i);
+        for (int j = j0 + w; j < ncol; j += 32) {
+            const double v = rowp[(long)j * ld];
+            sn = fma(v, v, sn);
+            if (zb) sd = fma(v, zb[(long)j * zstride], sd);
+        }
     }
-    out[i] = s;
-}
-
-// out[i] = sum_j M(row0+i, j) z[j*zstride]
-__global__ void rowgemv_kernel(const double* M, long ld, int row0, int nrow, int ncol, int jstart_by_row,
-                               const double* z, long zstride, double* out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrow) return;
-    double s = 0.0;
-    const int j0 = jstart_by_row ? (i / FGP_TILE) * FGP_TILE : 0;
-    for (int j = j0; j < ncol; ++j) s = fma(M[(long)(row0 + i) + (long)j * ld], z[(long)j * zstride], s);
-    out[i] = s;
+    redN[w][lane] = sn; redD[w][lane] = sd;
+    __syncthreads();
+    if (w == 0 && i < nrow) {
+        double a = 0.0, c = 0.0;
+        for (int q = 0; q < 32; ++q) { a += redN[q][lane]; c += redD[q][lane]; }
+        if (norm) norm[(long)blockIdx.y * nrow + i] = a;
+        if (dot) dot[(long)blockIdx.y * nrow + i] = c;
+    }
 }
 
 // sims(s, i) = mean[i] + sum_{j<=i} Lc(i,j) Z(j,s)    (R/5_simulation_SF.R:14-15), sims is nsim x m col-major
 __global__ void lower_times_kernel(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean,
                                    double* sims) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
     if (i >= m) return;
-    double acc = 0.0;
-    const double* z = Z + (long)s * m;
-    for (int j = 0; j <= i; ++j) acc = fma(Lc[(long)i + (long)j * ld], z[j], acc);
-    sims[(long)s + (long)i * nsim] = mean[i] + acc;
+    for (int s = blockIdx.y; s < nsim; s += gridDim.y) {
+        double acc = 0.0;
+        const double* z = Z + (long)s * m;
+        for (int j = 0; j <= i; ++j) acc = fma(Lc[(long)i + (long)j * ld], z[j], acc);
+        sims[(long)s + (long)i * nsim] = mean[i] + acc;
+    }
 }
 
 __global__ void extract_lower_kernel(const double* M, long ld, int n, double* out) {
@@ -310,14 +324,19 @@ __global__ void fill_yrow_kernel(double* M, long ld, long strideM, int row, cons
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) M[(long)blockIdx.y * strideM + (long)row + (long)j * ld] = y[j];
 }
+// heterogeneous batch: every element brings its own output vector
+__global__ void fill_yrow_elems_kernel(double* M, long ld, long strideM, int row, const AsmElem* elems, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) M[(long)blockIdx.y * strideM + (long)row + (long)j * ld] = elems[blockIdx.y].y[j];
+}
 
 // identity rows for LOOCV: rows row0 .. row0+n-1 (all columns: the wide trailing update reads rows that have not
 // started yet and needs zeros there)
 __global__ void fill_identity_rows_kernel(double* M, long ld, long strideM, int row0, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // extra row index
-    const int j = blockIdx.y;                               // column
     if (i >= n) return;
-    M[(long)blockIdx.z * strideM + (long)(row0 + i) + (long)j * ld] = (i == j) ? 1.0 : 0.0;
+    for (int j = blockIdx.y; j < n; j += gridDim.y)         // column
+        M[(long)blockIdx.z * strideM + (long)(row0 + i) + (long)j * ld] = (i == j) ? 1.0 : 0.0;
 }
 
 }  // namespace
@@ -327,18 +346,27 @@ void launch_nll_reduce(const double* M, long ld, long strideM, int batch, int n,
     FGP_COUNT_LAUNCH();
     nll_reduce_kernel<<<batch, 256, 0, st>>>(M, ld, strideM, n, yrow, var_known, info, nll, sig2);
 }
-void launch_rownorm2(const double* M, long ld, int row0, int nrow, int ncol, int upper, double* out, cudaStream_t st) {
+void launch_rownorm2(const double* M, long ld, long strideM, int batch, int row0, int nrow, int ncol, int upper, double* out,
+                     cudaStream_t st) {
+    if (nrow <= 0 || batch <= 0) return;
     FGP_COUNT_LAUNCH();
-    rownorm2_kernel<<<cdiv(nrow, 128), 128, 0, st>>>(M, ld, row0, nrow, ncol, upper, out);
+    rowstats_kernel<<<dim3(cdiv(nrow, 32), batch), 1024, 0, st>>>(M, ld, strideM, row0, nrow, ncol, upper, nullptr, 0, 0, out, nullptr);
 }
-void launch_rowgemv(const double* M, long ld, int row0, int nrow, int ncol, int upper, const double* z, long zstride,
-                    double* out, cudaStream_t st) {
+void launch_rowgemv(const double* M, long ld, long strideM, int batch, int row0, int nrow, int ncol, int upper,
+                    const double* z, long zstride, long zbatch, double* out, cudaStream_t st) {
+    if (nrow <= 0 || batch <= 0) return;
     FGP_COUNT_LAUNCH();
-    rowgemv_kernel<<<cdiv(nrow, 128), 128, 0, st>>>(M, ld, row0, nrow, ncol, upper, z, zstride, out);
+    rowstats_kernel<<<dim3(cdiv(nrow, 32), batch), 1024, 0, st>>>(M, ld, strideM, row0, nrow, ncol, upper, z, zstride, zbatch, nullptr, out);
+}
+void launch_rowstats(const double* M, long ld, long strideM, int batch, int row0, int nrow, int ncol, int upper,
+                     const double* z, long zstride, long zbatch, double* norm, double* dot, cudaStream_t st) {
+    if (nrow <= 0 || batch <= 0) return;
+    FGP_COUNT_LAUNCH();
+    rowstats_kernel<<<dim3(cdiv(nrow, 32), batch), 1024, 0, st>>>(M, ld, strideM, row0, nrow, ncol, upper, z, zstride, zbatch, norm, dot);
 }
 void launch_lower_times(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean, double* sims,
                         cudaStream_t st) {
-    dim3 grid(cdiv(m, 128), nsim);
+    dim3 grid(cdiv(m, 128), std::min(nsim, 65535));
     FGP_COUNT_LAUNCH();
     lower_times_kernel<<<grid, 128, 0, st>>>(Lc, ld, m, Z, nsim, mean, sims);
 }
@@ -352,8 +380,13 @@ void launch_fill_yrow(double* M, long ld, long strideM, int batch, int row, cons
     FGP_COUNT_LAUNCH();
     fill_yrow_kernel<<<grid, 256, 0, st>>>(M, ld, strideM, row, y, n);
 }
+void launch_fill_yrow_elems(double* M, long ld, long strideM, int batch, int row, const AsmElem* elems, int n, cudaStream_t st) {
+    dim3 grid(cdiv(n, 256), batch);
+    FGP_COUNT_LAUNCH();
+    fill_yrow_elems_kernel<<<grid, 256, 0, st>>>(M, ld, strideM, row, elems, n);
+}
 void launch_fill_identity_rows(double* M, long ld, long strideM, int batch, int row0, int n, cudaStream_t st) {
-    dim3 grid(cdiv(n, 128), n, batch);
+    dim3 grid(cdiv(n, 128), std::min(n, 65535), batch);
     FGP_COUNT_LAUNCH();
     fill_identity_rows_kernel<<<grid, 128, 0, st>>>(M, ld, strideM, row0, n);
 }

@@ -46,6 +46,17 @@ struct FgpUnit {
     int last;
 };
 
+// one element of a heterogeneous batch (fitlock.cu: the pending likelihood points of MANY candidate structures in one
+// launch): its own coordinate matrix, unit table, length-scale multipliers and output vector.  All elements share n.
+struct AsmElem {
+    const double* X;          // n x ncoord, leading dimension = AsmArgs::ldP
+    const FgpUnit* units;
+    const double* scale;      // nterms multipliers of THIS element
+    const double* y;          // output vector for the y row
+    int nunits;
+    int pad_;
+};
+
 struct AsmArgs {
     // row points P, column points Q (column-major coordinate matrices, leading dims ldP / ldQ)
     const double* XP; int nP; long ldP;
@@ -60,6 +71,7 @@ struct AsmArgs {
     double* M; long ld; long strideM;   // destination (+ batch stride); element (rowOff+i, colOff+j)
     int rowOff, colOff;
     int mirror;               // sym only: also write the transposed tile (full symmetric output)
+    const AsmElem* elems;     // non-null: batch element b takes XP = XQ, units and scale from elems[b] (sym only)
 };
 
 void launch_assemble(const AsmArgs& a, int batch, cudaStream_t st);
@@ -69,6 +81,7 @@ void launch_distmax(const double* X, int n, long ldX, const FgpUnit* units, int 
 void launch_distmat(const double* X, int n, long ldX, const FgpUnit* units, int u0, int u1, double* out, long ld,
                     cudaStream_t st);
 void launch_fill_yrow(double* M, long ld, long strideM, int batch, int row, const double* y, int n, cudaStream_t st);
+void launch_fill_yrow_elems(double* M, long ld, long strideM, int batch, int row, const AsmElem* elems, int n, cudaStream_t st);
 void launch_fill_identity_rows(double* M, long ld, long strideM, int batch, int row0, int n, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
@@ -118,9 +131,14 @@ void launch_gemm(const GemmArgs& g, cudaStream_t st);
 void launch_nll_reduce(const double* M, long ld, long strideM, int batch, int n, int yrow, const double* var_known,
                        const int* info, double* nll, double* sig2, cudaStream_t st);
 // generic small kernels used by predict / simulate / loocv
-void launch_rownorm2(const double* M, long ld, int row0, int nrow, int ncol, int upper, double* out, cudaStream_t st);
-void launch_rowgemv(const double* M, long ld, int row0, int nrow, int ncol, int upper, const double* z, long zstride,
-                    double* out, cudaStream_t st);
+// out[b*nrow + i] = sum_j M_b(row0+i, j)^2 and sum_j M_b(row0+i, j) z_b[j*zstride]; one warp per row, fixed summation
+// order; `upper`: columns before the row's own tile are known zeros (LOOCV's L^-T) and skipped
+void launch_rownorm2(const double* M, long ld, long strideM, int batch, int row0, int nrow, int ncol, int upper, double* out,
+                     cudaStream_t st);
+void launch_rowgemv(const double* M, long ld, long strideM, int batch, int row0, int nrow, int ncol, int upper,
+                    const double* z, long zstride, long zbatch, double* out, cudaStream_t st);
+void launch_rowstats(const double* M, long ld, long strideM, int batch, int row0, int nrow, int ncol, int upper,
+                     const double* z, long zstride, long zbatch, double* norm, double* dot, cudaStream_t st);
 void launch_lower_times(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean, double* sims,
                         cudaStream_t st);
 void launch_extract_lower(const double* M, long ld, int n, double* out, cudaStream_t st);
@@ -131,3 +149,7 @@ int fgp_peaks_device(double* dmma_tflops, double* dfma_tflops, double* copy_gbs)
 #include <atomic>
 extern std::atomic<long long> g_fgp_launches;
 #define FGP_COUNT_LAUNCH() (g_fgp_launches.fetch_add(1, std::memory_order_relaxed))
+// work items of the process (bench.py turns them into aggregate FLOP/s): [0] likelihood factorisations (n^3/3 each),
+// [1] leave-one-out factorisations (Cholesky + L^-T: 2 n^3/3), [2] preMats factorisations, [3] candidates scored
+extern std::atomic<long long> g_fgp_work[4];
+#define FGP_COUNT_WORK(i, k) (g_fgp_work[i].fetch_add((k), std::memory_order_relaxed))

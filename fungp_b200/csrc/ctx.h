@@ -101,7 +101,11 @@ struct fgp_ctx {
     int profile = 0;
     int lookahead = 1;
     int streams = 8;
-    int fit_workers = 8;      // fgp_fit_batch: concurrent candidate fits per GPU
+    int fit_workers = 8;      // fgp_fit_batch, fit_mode 0: concurrent candidate fits (host threads) per GPU
+    int fit_mode = 1;         // 1: lock-step -- one host thread per GPU advances all in-flight candidates together (fitlock.cu); 0: one thread per candidate
+    int fit_points = 0;       // lock-step: likelihood points per round and lane (0 = by memory, at most 512)
+    int fit_lanes = 0;        // lock-step: rounds in flight per GPU (0 = 2 below n = 2048, else 1)
+    int predict_reserve = 2048;   // rows kept free under the stored factor so that predict / simulate solve in place
     int graphs = 0;           // option "graphs": replay small-n likelihood calls as CUDA graphs (second call onwards)
     int blockingSync = 0;     // host waits sleep instead of spinning (set on fit_batch worker contexts)
     int fit_blocking = -1;    // option "fit_blocking": worker contexts of fgp_fit_batch use blocking waits (-1 = auto)
@@ -112,7 +116,20 @@ struct fgp_ctx {
     // fgp_fit_batch: worker contexts (one per device and worker slot), created on first use and kept: creating streams
     // and workspaces per call cost more than a candidate at n = 1024
     std::vector<fgp_ctx*> fitWorkers;
+    // lock-step driver state of a worker context (streams, pinned staging, workspaces), released with the context
+    void* lockState = nullptr;
+    void (*lockFree)(void*) = nullptr;
 };
+
+static inline long fgp_roundup(long a, long b) { return (a + b - 1) / b * b; }
+// leading dimension: multiple of 16 doubles (128 B); avoid large power-of-two strides
+static inline long fgp_pick_ld(long rows) {
+    long ld = fgp_roundup(rows, 16);
+    if (ld % 512 == 0) ld += 16;
+    return ld;
+}
+// host wait for a stream honouring the context's waiting policy (spin / blocking event / poll-and-yield), api.cu
+cudaError_t fgp_wait_stream(fgp_ctx* ctx, DevState& d, cudaStream_t st);
 
 // a captured launch sequence of one batched likelihood call (small n: one stream, ~26 launches), see nll_range
 struct NllGraph {

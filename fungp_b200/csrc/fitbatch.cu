@@ -7,123 +7,49 @@
 // L-BFGS-B of lbfgsb.hpp with one batched device call per iterate (value + 2d finite-difference neighbours).
 // Candidates are independent: they are dealt from a queue to worker threads, `fit_workers` per GPU of the context,
 // each with its own streams and workspaces, so small-n fits overlap on the chip and GPUs never exchange data.
-#include "ctx.h"
+#include "fitcommon.h"
 #include "lbfgsb.hpp"
-#include "../../include/fungp_b200.h"
-#include <atomic>
 #include <cstdlib>
 #include <cstring>
-#include <map>
 #include <thread>
-#include <tuple>
+
+using namespace fgp_fit;
 
 namespace {
 
-struct Proj { std::vector<double> B, J, coefs, coefsVl; int pe = 0; bool ok = false; };
-
-struct Shared {
-    int n, ds, df;
-    const double* sIn; const int* k; const double* const* fIn; const double* y;
-    int n_cand, antLen; const int* ants;
-    double nugget; int n_starts, n_presample;
-    const double* u01; const long long* u01_off; int dmax;
-    double *fitness, *nll, *sig2, *theta; int* info;
-    // hold-out validation (eval_houtv_ACO): n_rep splits, n_vl validation rows each (1-based row indices, column-major
-    // n_vl x n_rep); n_rep = 0 -> leave-one-out fitness on the full data
-    int n_rep = 0, n_vl = 0; const int* ind_vl = nullptr;
-    std::vector<std::vector<int>> trRows, vlRows;       // per replicate: 0-based training / validation rows
-    std::vector<std::vector<double>> yTr, yVl;
-    std::mutex mu;
-    std::map<std::tuple<int, int, int, int>, Proj> cache;    // (input, p, basis, replicate) -> projection, shared by all items
-    std::atomic<int> next{0};
-    std::atomic<int> failures{0};
-};
-
-// gather rows of a column-major n x k matrix
-std::vector<double> take_rows(const double* M, int n, int k, const std::vector<int>& rows) {
-    std::vector<double> out((size_t)rows.size() * k);
-    for (int c = 0; c < k; ++c)
-        for (size_t r = 0; r < rows.size(); ++r) out[r + (size_t)c * rows.size()] = M[rows[r] + (size_t)c * n];
-    return out;
-}
-
-// dimReduction of input j on the training rows of replicate `rep` (-1: all rows) and, for a hold-out split, the
-// projection of the validation curves with the same basis (R/1_fgpm_Class.R:844-845)
-const Proj& projection(Shared& S, int j, int p, int basis, int rep) {
-    std::lock_guard<std::mutex> lk(S.mu);
-    auto key = std::make_tuple(j, p, basis, rep);
-    auto it = S.cache.find(key);
-    if (it != S.cache.end()) return it->second;
-    Proj pr;
-    const int kk = S.k[j];
-    pr.pe = p ? p : kk;
-    pr.B.resize((size_t)kk * pr.pe); pr.J.resize((size_t)pr.pe * pr.pe);
-    if (rep < 0) {
-        pr.coefs.resize((size_t)S.n * pr.pe);
-        pr.ok = fgp_project(nullptr, S.fIn[j], S.n, kk, p, basis, nullptr, pr.B.data(), pr.J.data(), pr.coefs.data()) == 0;
-    } else {
-        const std::vector<double> ftr = take_rows(S.fIn[j], S.n, kk, S.trRows[rep]), fvl = take_rows(S.fIn[j], S.n, kk, S.vlRows[rep]);
-        const int ntr = (int)S.trRows[rep].size(), nvl = (int)S.vlRows[rep].size();
-        pr.coefs.resize((size_t)ntr * pr.pe); pr.coefsVl.resize((size_t)nvl * pr.pe);
-        std::vector<double> Jtmp((size_t)pr.pe * pr.pe), Btmp((size_t)kk * pr.pe);
-        pr.ok = fgp_project(nullptr, ftr.data(), ntr, kk, p, basis, nullptr, pr.B.data(), pr.J.data(), pr.coefs.data()) == 0 &&
-                fgp_project(nullptr, fvl.data(), nvl, kk, p, basis, p ? pr.B.data() : nullptr, Btmp.data(), Jtmp.data(), pr.coefsVl.data()) == 0;
-    }
-    return S.cache.emplace(key, std::move(pr)).first->second;
-}
-
-void crash(Shared& S, int c, int code) {
-    S.fitness[c] = std::nan(""); S.nll[c] = std::nan(""); S.sig2[c] = std::nan("");
-    for (int i = 0; i < S.dmax; ++i) S.theta[(size_t)c * S.dmax + i] = std::nan("");
-    S.info[c] = code;
-}
-
 void fit_one(Shared& S, fgp_ctx* ctx, int item) {
-    const int nrep = std::max(1, S.n_rep);
-    const int cand = item / nrep, rep = S.n_rep > 0 ? item % nrep : -1;
     const int c = item;                 // output slot
-    const int* ant = S.ants + (size_t)cand * S.antLen;
-    const int n = rep < 0 ? S.n : (int)S.trRows[rep].size();
-    const double* yv = rep < 0 ? S.y : S.yTr[rep].data();
     // ---- formatSol_ACO
+    const Decoded D = decode_item(S, ctx, item);
+    if (D.code) { crash(S, c, D.code); return; }
+    const int rep = D.rep, n = D.n, ker = D.ker, dsA = D.dsA, dfA = D.dfA;
+    const double* yv = rep < 0 ? S.y : S.yTr[rep].data();
     std::vector<double> sAct, sVl;
-    int dsA = 0;
-    for (int i = 0; i < S.ds; ++i)
-        if (ant[i] == 1) {
-            if (rep < 0) sAct.insert(sAct.end(), S.sIn + (size_t)i * S.n, S.sIn + (size_t)(i + 1) * S.n);
-            else {
-                for (int r : S.trRows[rep]) sAct.push_back(S.sIn[r + (size_t)i * S.n]);
-                for (int r : S.vlRows[rep]) sVl.push_back(S.sIn[r + (size_t)i * S.n]);
-            }
-            ++dsA;
+    for (int i : D.sIdx) {
+        if (rep < 0) sAct.insert(sAct.end(), S.sIn + (size_t)i * S.n, S.sIn + (size_t)(i + 1) * S.n);
+        else {
+            for (int r : S.trRows[rep]) sAct.push_back(S.sIn[r + (size_t)i * S.n]);
+            for (int r : S.vlRows[rep]) sVl.push_back(S.sIn[r + (size_t)i * S.n]);
         }
-    std::vector<const double*> coefsVl;
-    std::vector<const double*> coefs, Js;
-    std::vector<int> p, dis;
-    for (int j = 0; j < S.df; ++j) {
-        const int* a = ant + S.ds + 4 * j;
-        if (a[0] != 1) continue;
-        const int dist = a[1], dim = a[2], bas = (a[3] == FGP_BASIS_PCA) ? FGP_BASIS_PCA : FGP_BASIS_BSPLINES;
-        if ((dist != FGP_DIST_BYGROUP && dist != FGP_DIST_BYINDEX) || dim < 0 || dim > S.k[j]) { crash(S, c, -1); return; }
-        const Proj& pr = projection(S, j, dim, bas, rep);
-        if (!pr.ok) { crash(S, c, -2); return; }
-        coefs.push_back(pr.coefs.data()); Js.push_back(pr.J.data()); p.push_back(pr.pe); dis.push_back(dist);
-        coefsVl.push_back(pr.coefsVl.data());
     }
-    const int ker = ant[S.antLen - 1];
-    const int dfA = (int)coefs.size();
-    if ((dsA == 0 && dfA == 0) || ker < 1 || ker > 3) { crash(S, c, -1); return; }
+    std::vector<const double*> coefs, Js, coefsVl;
+    for (const Proj* pr : D.proj) { coefs.push_back(pr->coefs.data()); Js.push_back(pr->J.data()); coefsVl.push_back(pr->coefsVl.data()); }
+    const std::vector<int>& p = D.p;
+    const std::vector<int>& dis = D.dis;
 
     fgp_problem* P = nullptr;
-    if (fgp_problem_create(ctx, n, dsA, dsA ? sAct.data() : nullptr, dfA, p.data(), dis.data(), coefs.data(), Js.data(), yv, &P)) {
-        crash(S, c, -3); return;
-    }
+    int rc = fgp_problem_create(ctx, n, dsA, dsA ? sAct.data() : nullptr, dfA, p.data(), dis.data(), coefs.data(), Js.data(), yv, &P);
+    if (rc) { S.infra(rc, ctx); crash(S, c, -3); return; }
     const int d = fgp_problem_nls(P);
-    auto done = [&](int code) { if (code) crash(S, c, code); fgp_problem_destroy(P); };
+    auto done = [&](int code) {
+        if (code == -3) S.infra(rc < 0 ? rc : FGP_ERR_CUDA, ctx);     // the library itself failed: not a model crash
+        if (code) crash(S, c, code);
+        fgp_problem_destroy(P);
+    };
     if (d > S.dmax) { done(-4); return; }
     // ---- setBounds_*: lower 1e-10, upper 2 max(D_l)
     std::vector<double> lo(d, 1e-10), up(d);
-    if (fgp_dist_max(P, up.data())) { done(-3); return; }
+    if ((rc = fgp_dist_max(P, up.data()))) { done(-3); return; }
     for (int i = 0; i < d; ++i) up[i] *= 2.0;
     // ---- setSPoints_*: the presample draws were made by the caller (R's runif, in ant order)
     const int npre = std::max(S.n_presample, S.n_starts);
@@ -132,7 +58,7 @@ void fit_one(Shared& S, fgp_ctx* ctx, int item) {
     std::vector<int> inf(npre);
     for (int j = 0; j < npre; ++j)
         for (int i = 0; i < d; ++i) pts[i + (size_t)j * d] = lo[i] + u[i + (size_t)j * d] * (up[i] - lo[i]);
-    if (fgp_nll_batch(P, ker, S.nugget, npre, pts.data(), nullptr, v.data(), s2.data(), inf.data())) { done(-3); return; }
+    if ((rc = fgp_nll_batch(P, ker, S.nugget, npre, pts.data(), nullptr, v.data(), s2.data(), inf.data()))) { done(-3); return; }
     for (int j = 0; j < npre; ++j)
         if (inf[j]) { done(inf[j]); return; }       // quirk Q6: a chol failure while presampling aborts the fit
     std::vector<int> ord(npre);
@@ -142,6 +68,7 @@ void fit_one(Shared& S, fgp_ctx* ctx, int item) {
     const int nfd = 2 * d + 1;
     std::vector<double> fdp((size_t)d * nfd), fv(nfd), fs(nfd);
     std::vector<int> fi(nfd);
+    bool infra = false;
     fgp_lbfgsb::FG fg = [&](const std::vector<double>& x, double& f, std::vector<double>& g) {
         for (int j = 0; j < nfd; ++j)
             for (int i = 0; i < d; ++i) fdp[i + (size_t)j * d] = x[i];
@@ -149,7 +76,7 @@ void fit_one(Shared& S, fgp_ctx* ctx, int item) {
             fdp[i + (size_t)(1 + 2 * i) * d] = std::min(x[i] + 1e-3, up[i]);
             fdp[i + (size_t)(2 + 2 * i) * d] = std::max(x[i] - 1e-3, lo[i]);
         }
-        if (fgp_nll_batch(P, ker, S.nugget, nfd, fdp.data(), nullptr, fv.data(), fs.data(), fi.data())) return false;
+        if ((rc = fgp_nll_batch(P, ker, S.nugget, nfd, fdp.data(), nullptr, fv.data(), fs.data(), fi.data()))) { infra = true; return false; }
         for (int j = 0; j < nfd; ++j)
             if (fi[j] || !std::isfinite(fv[j])) return false;
         f = fv[0];
@@ -164,31 +91,35 @@ void fit_one(Shared& S, fgp_ctx* ctx, int item) {
     for (int sI = 0; sI < S.n_starts; ++sI) {
         std::vector<double> x(pts.begin() + (size_t)ord[sI] * d, pts.begin() + (size_t)(ord[sI] + 1) * d);
         fgp_lbfgsb::Result r = fgp_lbfgsb::minimize(fg, x, lo, up);
-        if (r.failed_eval && r.nfev <= 1) continue;          // tryCatch per start (R/3_training_SF.R:141-153)
+        if (infra) { done(-3); return; }
+        // Any error inside optim() aborts that start: the reference wraps every start in tryCatch when n.starts > 1
+        // (R/3_training_SF.R:141-153) and, with a single start, lets the error reach fitNtests_ACO, which logs the ant as
+        // a crash (R/3_ant_admin.R:815-829).  A not-positive-definite trial point or finite-difference neighbour therefore
+        // never leaves a half-optimised iterate behind.
+        if (r.failed_eval) continue;
         if (!have || r.f < bestf) { have = true; bestf = r.f; bestx = x; }
     }
     if (!have) { done(-5); return; }                        // "All model optimizations crashed!"
     // ---- variance at the optimum, preMats, Q2loocv
-    double f1, s1; int i1;
-    if (fgp_nll_batch(P, ker, S.nugget, 1, bestx.data(), nullptr, &f1, &s1, &i1) || i1) { done(i1 ? i1 : -3); return; }
-    int rc = fgp_premats(P, ker, S.nugget, s1, bestx.data(), nullptr, nullptr);
-    if (rc) { done(rc); return; }
+    double f1, s1; int i1 = 0;
+    if ((rc = fgp_nll_batch(P, ker, S.nugget, 1, bestx.data(), nullptr, &f1, &s1, &i1)) || i1) { done(i1 ? i1 : -3); return; }
     double q2 = 0.0;
     if (rep < 0) {
-        rc = fgp_loocv(P, nullptr, &q2);                       // Q2loocv (R/1_Xfgpm_Class.R:539-542)
-        if (rc) { done(rc); return; }
+        // Q2loocv (R/1_Xfgpm_Class.R:539-542).  getOut_loocv rebuilds R from the hyper-parameters, so the candidate's
+        // preMats are only materialised for hold-out scoring (the caller rebuilds the winner's model from theta, sig2)
+        rc = fgp_premats(P, ker, S.nugget, s1, bestx.data(), nullptr, nullptr);
+        if (rc) { done(rc > 0 ? rc : -3); return; }
+        rc = fgp_loocv(P, nullptr, &q2);
+        if (rc) { done(rc > 0 ? rc : -3); return; }
     } else {
+        rc = fgp_premats(P, ker, S.nugget, s1, bestx.data(), nullptr, nullptr);
+        if (rc) { done(rc > 0 ? rc : -3); return; }
         // Q2hout: predict the validation rows (R/1_Xfgpm_Class.R:545-549)
         const int nvl = (int)S.vlRows[rep].size();
         std::vector<double> mean(nvl), sd(nvl);
         rc = fgp_predict(P, nvl, dsA ? sVl.data() : nullptr, coefsVl.data(), FGP_DETAIL_LIGHT, mean.data(), sd.data(), nullptr, nullptr);
-        if (rc) { done(rc); return; }
-        const std::vector<double>& yvl = S.yVl[rep];
-        double mu = 0.0, se = 0.0, st = 0.0;
-        for (int i = 0; i < nvl; ++i) mu += yvl[i];
-        mu /= nvl;
-        for (int i = 0; i < nvl; ++i) { se += (yvl[i] - mean[i]) * (yvl[i] - mean[i]); st += (yvl[i] - mu) * (yvl[i] - mu); }
-        q2 = 1.0 - (se / nvl) / (st / nvl);
+        if (rc) { done(rc > 0 ? rc : -3); return; }
+        q2 = q2_of(S.yVl[rep].data(), mean.data(), nvl);
     }
     S.fitness[c] = q2; S.nll[c] = bestf; S.sig2[c] = s1; S.info[c] = 0;
     for (int i = 0; i < S.dmax; ++i) S.theta[(size_t)c * S.dmax + i] = i < d ? bestx[i] : std::nan("");
@@ -246,6 +177,13 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
         nls[it] = d;
     }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nls[a] > nls[b]; });
+    if (ctx->fit_mode == 1) {
+        const int rcl = fit_lockstep(ctx, S, order);
+        cudaSetDevice(ctx->dev[0].device);
+        if (rcl) return rcl;
+        if (S.infraErr.load()) { fgp_set_err(ctx, "fgp_fit_batch: " + S.infraMsg); return S.infraErr.load(); }
+        return 0;
+    }
     std::vector<std::thread> th;
     std::atomic<int> ctxFail{0};
     // How the workers wait on the host: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 poll the event
@@ -282,6 +220,7 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
                     const int q = S.next.fetch_add(1);
                     if (q >= n_items) break;
                     fit_one(S, wc, order[q]);
+                    FGP_COUNT_WORK(3, 1);
                 }
                 // large workspaces go back to the device (candidates at n = 8192 need GBs per worker); small ones stay
                 DevState& d = wc->dev[0];
@@ -292,6 +231,7 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
     cudaSetDevice(ctx->dev[0].device);
     if (ctxFail.load() == nd * wpd && n_items > 0) { fgp_set_err(ctx, "fgp_fit_batch: no worker context could be created"); return FGP_ERR_CUDA; }
     if (S.next.load() < n_items) { fgp_set_err(ctx, "fgp_fit_batch: workers stopped early"); return FGP_ERR_CUDA; }
+    if (S.infraErr.load()) { fgp_set_err(ctx, "fgp_fit_batch: " + S.infraMsg); return S.infraErr.load(); }
     return 0;
 }
 

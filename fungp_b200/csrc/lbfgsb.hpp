@@ -161,23 +161,71 @@ struct MTSearch {
 
 }  // namespace detail
 
-// minimise fg over the box [lo, up]; x holds the start and returns the solution
-inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<double>& lo, const std::vector<double>& up,
-                       int lmm = 5, double factr = 1e7, double pgtol = 0.0, int maxit = 100) {
-    using namespace detail;
-    const int n = (int)x.size();
-    const double epsmch = std::numeric_limits<double>::epsilon();
-    const double tol = factr * epsmch;
-    const double INF = std::numeric_limits<double>::infinity();
+// L-BFGS-B in reverse communication: the caller evaluates f and the gradient wherever the machine asks.
+//   Machine m; m.init(x0, lo, up);  while (!m.done) { evaluate at m.x; m.feed(ok, f, g); }   -> m.x, m.res
+// This is what lets ONE host thread advance the fits of many candidate structures in lock-step (fitlock.cu): every
+// round the pending points of all machines go to the device in a single batched launch sequence.  minimize() below is
+// the same machine driven by a callback, so both callers run identical arithmetic.
+struct Machine {
     Result res;
-    for (int i = 0; i < n; ++i) x[i] = std::min(std::max(x[i], lo[i]), up[i]);   // project the start onto the box
-    std::vector<double> g(n), xold(n), gold(n), d(n), xc(n), z(n), t(n);
-    std::vector<std::vector<double>> S, Y;     // correction pairs, oldest first
-    double theta = 1.0, f = 0.0;
-    if (!fg(x, f, g)) { res.failed_eval = true; res.convergence = 52; return res; }
-    res.nfev = 1;
+    std::vector<double> x;          // where f and g are needed next; the solution once `done`
+    bool done = false;
 
-    auto proj_grad_norm = [&]() {
+    void init(const std::vector<double>& x0, const std::vector<double>& lo_, const std::vector<double>& up_, int lmm_ = 5,
+              double factr = 1e7, double pgtol_ = 0.0, int maxit_ = 100) {
+        n = (int)x0.size();
+        lo = lo_; up = up_; lmm = lmm_; pgtol = pgtol_; maxit = maxit_;
+        epsmch = std::numeric_limits<double>::epsilon();
+        tol = factr * epsmch;
+        res = Result();
+        done = false;
+        x = x0;
+        for (int i = 0; i < n; ++i) x[i] = std::min(std::max(x[i], lo[i]), up[i]);   // project the start onto the box
+        g.assign(n, 0.0); xold.assign(n, 0.0); gold.assign(n, 0.0); d.assign(n, 0.0); xc.assign(n, 0.0); t.assign(n, 0.0);
+        S.clear(); Y.clear(); Minv.clear();
+        theta = 1.0; f = 0.0; col = 0; iter = 0;
+        state = ST_INIT;
+    }
+
+    // the evaluation at x: ok = false when the function cannot be evaluated there (not positive definite)
+    void feed(bool ok, double fnew, const std::vector<double>& gnew) {
+        using namespace detail;
+        if (done) return;
+        if (state == ST_INIT) {
+            if (!ok) { res.failed_eval = true; res.convergence = 52; done = true; return; }
+            f = fnew; g = gnew;
+            res.nfev = 1;
+            if (proj_grad_norm() <= pgtol) { res.f = f; done = true; return; }
+            next_direction();
+            return;
+        }
+        // ---- line search trial point
+        if (!ok) { res.failed_eval = true; res.convergence = 52; res.f = fold; x = xold; done = true; return; }
+        f = fnew; g = gnew;
+        ++res.nfev; ++ifun;
+        double gd = 0.0;
+        for (int i = 0; i < n; ++i) gd += g[i] * d[i];
+        const MTSearch::Status st = ls.advance(f, gd, stp);
+        if (st == MTSearch::CONVERGED || st == MTSearch::WARNING) { after_line_search(); return; }
+        if (ifun >= 20) {     // too many trial points
+            x = xold; g = gold; f = fold;
+            if (col == 0) { res.convergence = 52; finish(); return; }
+            restart_memory();
+            return;
+        }
+        trial_point();
+    }
+
+private:
+    enum { ST_INIT, ST_LS } state = ST_INIT;
+    int n = 0, lmm = 5, maxit = 100, col = 0, iter = 0, ifun = 0;
+    double epsmch = 0, tol = 0, pgtol = 0, theta = 1.0, f = 0, fold = 0, gdold = 0, stp = 1.0;
+    std::vector<double> lo, up, g, xold, gold, d, xc, t, xbar, Minv;
+    std::vector<std::vector<double>> S, Y;     // correction pairs, oldest first
+    detail::MTSearch ls;
+
+    void finish() { res.f = f; done = true; }
+    double proj_grad_norm() const {
         double nrm = 0.0;
         for (int i = 0; i < n; ++i) {
             double gi = g[i];
@@ -186,13 +234,9 @@ inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<d
             nrm = std::max(nrm, std::fabs(gi));
         }
         return nrm;
-    };
-    if (proj_grad_norm() <= pgtol) { res.f = f; return res; }
-
+    }
     // middle matrix M^-1 = [[-D, L'], [L, theta S'S]] (2col x 2col), rows of W = [Y theta*S]
-    std::vector<double> Minv;
-    int col = 0;
-    auto build_middle = [&]() {
+    void build_middle() {
         col = (int)S.size();
         const int k = 2 * col;
         Minv.assign((size_t)k * k, 0.0);
@@ -204,18 +248,31 @@ inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<d
                 if (i > j) { Minv[(col + i) * k + j] = sy; Minv[j * k + (col + i)] = sy; }   // L and L'
                 Minv[(col + i) * k + (col + j)] = theta * ss;
             }
-    };
-    auto wrow = [&](int i, std::vector<double>& w) {     // i-th row of W
+    }
+    void wrow(int i, std::vector<double>& w) const {     // i-th row of W
         w.resize(2 * col);
         for (int j = 0; j < col; ++j) { w[j] = Y[j][i]; w[col + j] = theta * S[j][i]; }
-    };
-    auto Mtimes = [&](std::vector<double> v) {           // M v  (solve with M^-1)
-        if (col) solve_small(Minv, 2 * col, v);
+    }
+    std::vector<double> Mtimes(std::vector<double> v) const {           // M v  (solve with M^-1)
+        if (col) detail::solve_small(Minv, 2 * col, v);
         return v;
-    };
+    }
+    void restart_memory() {
+        // not a descent direction / failed search: drop the memory and restart from steepest descent
+        S.clear(); Y.clear(); theta = 1.0; build_middle();
+        if (++res.iterations > 2 * maxit) { res.convergence = 52; finish(); return; }
+        next_direction();
+    }
+    void trial_point() {
+        for (int i = 0; i < n; ++i) x[i] = (stp == 1.0) ? xbar[i] : xold[i] + stp * d[i];
+        state = ST_LS;
+    }
 
-    for (int iter = 0;; ++iter) {
-        if (iter >= maxit) { res.convergence = 1; break; }
+    // generalized Cauchy point, subspace minimisation, start of the line search: leaves the first trial point in x
+    void next_direction() {
+        using namespace detail;
+        const double INF = std::numeric_limits<double>::infinity();
+        if (iter >= maxit) { res.convergence = 1; finish(); return; }
         // ---------------- generalized Cauchy point
         const int k = 2 * col;
         std::vector<double> p(k, 0.0), c(k, 0.0), wb;
@@ -273,7 +330,7 @@ inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<d
             for (int j = 0; j < k; ++j) c[j] += dtm * p[j];
         }
         // ---------------- subspace minimisation over the variables that are free at the Cauchy point
-        std::vector<double> xbar = xc;
+        xbar = xc;
         std::vector<int> freev;
         for (int i = 0; i < n; ++i)
             if (xc[i] > lo[i] && xc[i] < up[i]) freev.push_back(i);
@@ -328,14 +385,12 @@ inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<d
         // ---------------- line search along d = xbar - x
         double dnorm2 = 0.0, gd = 0.0;
         for (int i = 0; i < n; ++i) { d[i] = xbar[i] - x[i]; dnorm2 += d[i] * d[i]; gd += g[i] * d[i]; }
-        bool restart = false, abnormal = false;
-        double stp = 1.0, fold = f, gdold = gd;
+        stp = 1.0; fold = f; gdold = gd;
         xold = x; gold = g;
-        if (gd >= 0.0 || dnorm2 == 0.0) {
-            // not a descent direction: drop the memory and restart from steepest descent, or stop
-            if (col == 0) abnormal = true; else restart = true;
-        } else {
-            MTSearch ls;
+        bool bad = false;
+        if (gd >= 0.0 || dnorm2 == 0.0) bad = true;
+        else {
+            ls = MTSearch();
             double stpmx = 1.0;
             if (iter != 0) {
                 stpmx = 1e10;
@@ -346,34 +401,23 @@ inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<d
             }
             ls.stpmax = stpmx;
             stp = std::min(1.0, stpmx);
-            if (stp <= 0.0 || ls.start(f, gd, stp) == MTSearch::ERROR) {
-                if (col == 0) abnormal = true; else restart = true;
-            } else {
-                int ifun = 0;
-                for (;;) {
-                    for (int i = 0; i < n; ++i) x[i] = (stp == 1.0) ? xbar[i] : xold[i] + stp * d[i];
-                    if (!fg(x, f, g)) { res.failed_eval = true; res.convergence = 52; res.f = fold; x = xold; return res; }
-                    ++res.nfev; ++ifun;
-                    gd = 0.0;
-                    for (int i = 0; i < n; ++i) gd += g[i] * d[i];
-                    const MTSearch::Status st = ls.advance(f, gd, stp);
-                    if (st == MTSearch::CONVERGED || st == MTSearch::WARNING) break;
-                    if (ifun >= 20) {     // too many trial points
-                        x = xold; g = gold; f = fold;
-                        if (col == 0) abnormal = true; else restart = true;
-                        break;
-                    }
-                }
-            }
+            if (stp <= 0.0 || ls.start(f, gd, stp) == MTSearch::ERROR) bad = true;
         }
-        if (abnormal) { res.convergence = 52; break; }
-        if (restart) { S.clear(); Y.clear(); theta = 1.0; build_middle(); --iter; if (++res.iterations > 2 * maxit) { res.convergence = 52; break; } continue; }
+        if (bad) {
+            if (col == 0) { res.convergence = 52; finish(); return; }      // abnormal termination
+            restart_memory();
+            return;
+        }
+        ifun = 0;
+        trial_point();
+    }
+
+    // the line search has accepted x: convergence tests, BFGS update, next iteration
+    void after_line_search() {
         ++res.iterations;
-        // ---------------- convergence tests
-        if (proj_grad_norm() <= pgtol) break;
+        if (proj_grad_norm() <= pgtol) { finish(); return; }
         const double ddum = std::max({std::fabs(fold), std::fabs(f), 1.0});
-        if (fold - f <= tol * ddum) break;
-        // ---------------- BFGS update
+        if (fold - f <= tol * ddum) { finish(); return; }
         std::vector<double> s(n), y(n);
         double sy = 0.0, yy = 0.0;
         for (int i = 0; i < n; ++i) { s[i] = x[i] - xold[i]; y[i] = g[i] - gold[i]; sy += s[i] * y[i]; yy += y[i] * y[i]; }
@@ -384,9 +428,24 @@ inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<d
             theta = yy / sy;
             build_middle();
         }
+        ++iter;
+        next_direction();
     }
-    res.f = f;
-    return res;
+};
+
+// minimise fg over the box [lo, up]; x holds the start and returns the solution
+inline Result minimize(const FG& fg, std::vector<double>& x, const std::vector<double>& lo, const std::vector<double>& up,
+                       int lmm = 5, double factr = 1e7, double pgtol = 0.0, int maxit = 100) {
+    Machine m;
+    m.init(x, lo, up, lmm, factr, pgtol, maxit);
+    std::vector<double> g(x.size());
+    while (!m.done) {
+        double f = 0.0;
+        const bool ok = fg(m.x, f, g);
+        m.feed(ok, f, g);
+    }
+    x = m.x;
+    return m.res;
 }
 
 }  // namespace fgp_lbfgsb

@@ -4,9 +4,8 @@
 // Jacobi, LU with partial pivoting).
 // With a context the two contractions over the n curves run on the device -- the covariance of proj_pca
 // (R/7_dimRedFunctions.R:58) and the projection itself, written as coefs = f * (B J^-1) (:18-19) -- while the k x p
-// design matrix, the k x k eigen-decomposition and the p x p solve stay on the host (k <= a few hundred).  Without a
-// context (host-side callers: the candidate cache of fgp_fit_batch, the CPU gate of the tests) the same contractions
-// are plain loops.
+// design matrix, the k x k eigen-decomposition and the p x p solve stay on the host (k <= a few hundred).  fgp_project
+// requires a context; the context-free loops survive only behind the test-support symbol fgp_test_project_host.
 #include "../../include/fungp_b200.h"
 #include "ctx.h"
 #include <algorithm>
@@ -267,8 +266,8 @@ extern "C" int fgp_bspline_basis(int k, int p, double* B_out) {
     return 0;
 }
 
-extern "C" int fgp_project(fgp_ctx* ctx, const double* f, int n, int k, int p, int basis_type, const double* B_in,
-                           double* B_out, double* J_out, double* coefs_out) {
+static int project_impl(fgp_ctx* ctx, const double* f, int n, int k, int p, int basis_type, const double* B_in,
+                        double* B_out, double* J_out, double* coefs_out) {
     if (!f || n <= 0 || k <= 0 || p < 0 || p > k || !coefs_out) return FGP_ERR_ARG;
     if (p == 0) {   // R/7_dimRedFunctions.R:22-25
         if (B_out) { std::fill(B_out, B_out + (size_t)k * k, 0.0); for (int i = 0; i < k; ++i) B_out[i + (size_t)i * k] = 1.0; }
@@ -360,4 +359,19 @@ extern "C" int fgp_project(fgp_ctx* ctx, const double* f, int n, int k, int p, i
         for (int a = 0; a < p; ++a) coefs_out[r + (size_t)a * n] = rhs[a];
     }
     return 0;
+}
+
+// The product entry point always runs the contractions over the curves on the device: a context is required.
+extern "C" int fgp_project(fgp_ctx* ctx, const double* f, int n, int k, int p, int basis_type, const double* B_in,
+                           double* B_out, double* J_out, double* coefs_out) {
+    if (!ctx) return FGP_ERR_ARG;
+    return project_impl(ctx, f, n, k, p, basis_type, B_in, B_out, J_out, coefs_out);
+}
+
+// TEST SUPPORT ONLY (tests/test_cabi_and_host.py, runs without a GPU): the host-side pieces of dimReduction -- B-spline
+// design matrix, Jacobi eigenvectors, LU solve -- with the two contractions as plain loops, so that they can be checked
+// against the oracle and the reference's stored bases on a machine that has no device.  Nothing in the library calls it.
+extern "C" int fgp_test_project_host(const double* f, int n, int k, int p, int basis_type, const double* B_in,
+                                     double* B_out, double* J_out, double* coefs_out) {
+    return project_impl(nullptr, f, n, k, p, basis_type, B_in, B_out, J_out, coefs_out);
 }

@@ -56,6 +56,11 @@ int fgp_bspline_basis(int k, int p, double* B_out /* k*p */);
  * J = B'B, coefs = t(solve(J, B' f')).  B_out (k x p'), J_out (p' x p'), coefs_out (n x p'), p' = p ? p : k. */
 int fgp_project(fgp_ctx* ctx, const double* f, int n, int k, int p, int basis_type, const double* B_in,
                 double* B_out, double* J_out, double* coefs_out);
+/* Test support only -- never called by the library or the R glue: the host-side pieces of fgp_project (design matrix,
+ * eigenvectors, p x p solve) with the contractions over the curves as plain loops, so that the CPU test gate can check
+ * them against the oracle on a machine without a GPU.  fgp_project itself fails without a context. */
+int fgp_test_project_host(const double* f, int n, int k, int p, int basis_type, const double* B_in, double* B_out,
+                          double* J_out, double* coefs_out);
 
 /* ---- problem = what setDistMatrix_S / setDistMatrix_F are given (R/7_distanceFunctions.R:3-22) ---- */
 /* sIn n x ds (may be NULL when ds = 0); for each functional input i: coefs[i] n x p[i], J[i] p[i] x p[i],
@@ -146,6 +151,9 @@ int fgp_fit_batch_holdout(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
 int fgp_get_timing(fgp_ctx* ctx, double* out8);
 /* kernels of this library launched by the process so far */
 long long fgp_launch_count(void);
+/* work items of the process so far: which = 0 likelihood factorisations (n^3/3 flops each), 1 leave-one-out
+ * factorisations (Cholesky + L^-T, 2 n^3/3), 2 preMats factorisations, 3 candidates scored by fgp_fit_batch */
+long long fgp_work_count(int which);
 /* device-side stopwatch over all of the library's streams on device 0 (CUDA events): idx, i, j in 0..3 */
 int fgp_mark(fgp_ctx* ctx, int idx);
 int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);

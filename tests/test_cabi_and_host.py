@@ -54,7 +54,9 @@ def _project(lib, f, p, bt, B=None):
     f = np.asfortranarray(f); n, k = f.shape; pp = p or k
     Bo = np.zeros((k, pp), order="F"); J = np.zeros((pp, pp), order="F"); co = np.zeros((n, pp), order="F")
     dp = lambda a: a.ctypes.data_as(_lib.c_dp)
-    rc = lib.fgp_project(None, dp(f), n, k, p, bt, None if B is None else dp(np.asfortranarray(B)), dp(Bo), dp(J), dp(co))
+    # the product entry point needs a device context; the host pieces are reachable through the test-support symbol
+    assert lib.fgp_project(None, dp(f), n, k, p, bt, None, dp(Bo), dp(J), dp(co)) == -1
+    rc = lib.fgp_test_project_host(dp(f), n, k, p, bt, None if B is None else dp(np.asfortranarray(B)), dp(Bo), dp(J), dp(co))
     assert rc == 0
     return Bo, J, co
 

@@ -10,6 +10,7 @@ import os
 import numpy as np
 import pytest
 
+from oracle import fungp_ref as ref
 from oracle.rrng import RRng
 from helpers import load_models, GOLD, synth_problem
 
@@ -69,13 +70,25 @@ def test_fit_batch_vs_host_mirror_and_worker_independence(ctx):
         ker = ["gauss", "matern5_2", "matern3_2"][rng.integers(3)]
         ants.append(F.encode_ant(ds, 2, s_act, f_act, dis, pd, bas, ker))
     ants = np.stack(ants)
-    ctx.set_option("fit_workers", 4)
-    r4 = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(9), n_starts=2, n_presample=20)
-    ctx.set_option("fit_workers", 1)
-    r1 = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(9), n_starts=2, n_presample=20)
-    ctx.set_option("fit_workers", 4)
-    for key in ("fitness", "nll", "sig2", "theta"):
-        assert np.array_equal(r1[key], r4[key], equal_nan=True), key       # candidates are independent: bit-identical
+    try:
+        # one host thread per candidate (fit_mode 0), 4 and 1 worker contexts.  Look-ahead off: the thread path then
+        # factors its single-point calls with the same schedule as the batched rounds of the lock-step driver
+        ctx.set_option("fit_mode", 0); ctx.set_option("lookahead", 0)
+        ctx.set_option("fit_workers", 4)
+        r4 = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(9), n_starts=2, n_presample=20)
+        ctx.set_option("fit_workers", 1)
+        r1 = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(9), n_starts=2, n_presample=20)
+        # lock-step driver (fit_mode 1, the default): two lanes of up to 512 points, then one lane of 60 points
+        ctx.set_option("fit_mode", 1); ctx.set_option("lookahead", 1)
+        rl = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(9), n_starts=2, n_presample=20)
+        ctx.set_option("fit_points", 60); ctx.set_option("fit_lanes", 1)
+        rs = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(9), n_starts=2, n_presample=20)
+    finally:
+        for name, val in (("fit_mode", 1), ("lookahead", 1), ("fit_workers", 8), ("fit_points", 0), ("fit_lanes", 0)):
+            ctx.set_option(name, val)
+    for other in (r1, rl, rs):
+        for key in ("fitness", "nll", "sig2", "theta", "info"):
+            assert np.array_equal(other[key], r4[key], equal_nan=True), key     # items are independent: bit-identical
     assert (r4["info"] == 0).all()
     # the same candidates through the host mirror (scipy's L-BFGS-B), same R-compatible presample stream
     rr = RRng(9)
@@ -129,3 +142,106 @@ def test_holdout_fitness_vs_host_mirror(ctx):
             if abs(m.negLogLik - res["nll"][item]) <= 1e-5 * max(1.0, abs(m.negLogLik)):
                 assert abs(q2 - res["fitness"][item]) <= 2e-3, (item, q2, res["fitness"][item])
     assert np.all(np.isfinite(res["fitness_mean"]))
+
+
+def _fit_args(kw, sIn, fIn, rows=None):
+    rows = slice(None) if rows is None else rows
+    return dict(sIn=sIn[rows][:, kw["s_active"]] if kw["s_active"] else None,
+                fIn=[fIn[q][rows] for q in kw["f_active"]] if kw["f_active"] else None, kerType=kw["kerType"],
+                f_disType=kw["f_disType"] or "L2_bygroup", f_pdims=kw["f_pdims"] or 3, f_basType=kw["f_basType"] or "B-splines")
+
+
+def test_scores_vs_oracle_at_the_fitted_hypers(ctx):
+    """Parity of the SCORING arithmetic, independent of the optimiser: the oracle (oracle/fungp_ref.py, numpy/scipy) builds
+    the model at the hyper-parameters fgp_fit_batch returned (fgpm with known var / ls, R/3_training_SF.R:7-18) and computes
+    Q2loocv (R/8_outilsStats.R:1-7) and Q2hout (predict on the validation rows, R/1_Xfgpm_Class.R:545-549) itself."""
+    from fungp_b200 import factory as F
+    n, ds = 240, 2
+    sIn, fIn, y, _ = synth_problem(93, n, ds, [14, 18])
+    rng = np.random.default_rng(2)
+    ind_vl = np.stack([np.sort(rng.choice(n, 48, replace=False)) + 1 for _ in range(2)], axis=1)      # 48 x 2, 1-based
+    ants = np.stack([F.encode_ant(ds, 2, [0, 1], [0, 1], ["L2_bygroup", "L2_byindex"], [3, 2], ["B-splines", "B-splines"], "matern5_2"),
+                     F.encode_ant(ds, 2, [1], [1], ["L2_bygroup"], [4], ["B-splines"], "gauss"),
+                     F.encode_ant(ds, 2, [0, 1], [], [], [], [], "matern3_2")])
+    loo = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20)
+    hout = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20, ind_vl=ind_vl)
+    assert (loo["info"] == 0).all() and (hout["info"] == 0).all()
+    for c, ant in enumerate(ants):
+        kw = F.decode_ant(ant, ds, 2)
+        nsA = len(kw["s_active"])
+        th = loo["theta"][c][np.isfinite(loo["theta"][c])]
+        m = ref.fgpm(sOut=y, var_hyp=loo["sig2"][c], ls_s_hyp=th[:nsA] if nsA else None, ls_f_hyp=th[nsA:] if th.size > nsA else None,
+                     **_fit_args(kw, sIn, fIn))
+        assert abs(ref.q2_loocv(m) - loo["fitness"][c]) <= 1e-8, (c, ref.q2_loocv(m), loo["fitness"][c])
+        # the returned nll / sig2 are the oracle's at that theta
+        Ms = (ref.setDistMatrix_S(m.sIn, m.sIn) if m.ds else []) + (ref.setDistMatrix_F(m.coefs, m.coefs, m.J, m.f_disType) if m.df else [])
+        r_nll, r_s2 = ref.negLogLik(th, [], Ms, y, kw["kerType"], 1e-8)
+        assert abs(r_nll - loo["nll"][c]) <= 1e-9 * max(abs(r_nll), n) and abs(r_s2 - loo["sig2"][c]) <= 1e-8 * r_s2
+        for j in range(2):
+            vl = ind_vl[:, j] - 1
+            tr = np.setdiff1d(np.arange(n), vl)
+            item = c * 2 + j
+            th = hout["theta"][item][np.isfinite(hout["theta"][item])]
+            m = ref.fgpm(sOut=y[tr], var_hyp=hout["sig2"][item], ls_s_hyp=th[:nsA] if nsA else None,
+                         ls_f_hyp=th[nsA:] if th.size > nsA else None, **_fit_args(kw, sIn, fIn, tr))
+            pr = ref.predict(m, sNew=sIn[vl][:, kw["s_active"]] if kw["s_active"] else None,
+                             fNew=[fIn[q][vl] for q in kw["f_active"]] if kw["f_active"] else None)
+            q2 = ref.q2(y[vl], pr["mean"])
+            assert abs(q2 - hout["fitness"][item]) <= 1e-8, (item, q2, hout["fitness"][item])
+
+
+def test_holdout_fit_vs_oracle_fit(ctx):
+    """eval_houtv_ACO end to end against the ORACLE's own fit (ref.fgpm with scipy's L-BFGS-B on the numpy likelihood, same
+    R-compatible presample stream) + ref.predict on the split: where both optimisers stop in the same optimum the hold-out
+    Q2 agrees to optimiser tolerance."""
+    from fungp_b200 import factory as F
+    n, ds = 200, 2
+    sIn, fIn, y, _ = synth_problem(97, n, ds, [14, 18])
+    rng = np.random.default_rng(5)
+    ind_vl = np.sort(rng.choice(n, 40, replace=False))[:, None] + 1
+    ants = np.stack([F.encode_ant(ds, 2, [0, 1], [0], ["L2_bygroup"], [3], ["B-splines"], "matern5_2"),
+                     F.encode_ant(ds, 2, [0, 1], [], [], [], [], "matern3_2")])
+    res = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20, ind_vl=ind_vl)
+    rr = RRng(3)
+    vl = ind_vl[:, 0] - 1
+    tr = np.setdiff1d(np.arange(n), vl)
+    same = 0
+    for c, ant in enumerate(ants):
+        kw = F.decode_ant(ant, ds, 2)
+        m = ref.fgpm(sOut=y[tr], n_starts=2, n_presample=20, rng=rr, **_fit_args(kw, sIn, fIn, tr))
+        pr = ref.predict(m, sNew=sIn[vl][:, kw["s_active"]] if kw["s_active"] else None,
+                         fNew=[fIn[q][vl] for q in kw["f_active"]] if kw["f_active"] else None)
+        q2 = ref.q2(y[vl], pr["mean"])
+        if abs(m.negLogLik - res["nll"][c]) <= 1e-5 * max(1.0, abs(m.negLogLik)):
+            same += 1
+            assert abs(q2 - res["fitness"][c]) <= 2e-3, (c, q2, res["fitness"][c])
+    assert same >= 1
+
+
+def test_error_inside_the_search_is_a_crash(ctx):
+    """A not-positive-definite matrix met DURING L-BFGS-B (not while presampling): the reference's optim() raises, the
+    start is lost (tryCatch, R/3_training_SF.R:141-153) and with no start left fitNtests_ACO logs the ant as a crash
+    (R/3_ant_admin.R:815-829).  150 points on a line, gauss kernel, no nugget: the likelihood can be evaluated below
+    theta ~ 0.019 only (oracle: chol fails from 0.02 on) and decreases towards larger theta, so every start runs into it.
+    A well-posed candidate of the same call is not affected, and both drivers report the same."""
+    from fungp_b200 import factory as F
+    n = 150
+    x = np.linspace(0.0, 1.0, n)
+    sIn = np.stack([x, np.random.default_rng(0).random(n)], axis=1)
+    y = np.sin(3.0 * x)
+    ants = np.stack([F.encode_ant(2, 0, [0], [], [], [], [], "gauss"), F.encode_ant(2, 0, [0, 1], [], [], [], [], "matern3_2")])
+    u_small = 0.002 + 0.0025 * np.random.default_rng(1).random(20)        # presample thetas in [0.004, 0.009]: all fine
+    u_any = np.random.default_rng(2).random(40)                           # the oracle fits this one without an error
+    with pytest.raises(ref.NotPosDef):
+        ref.negLogLik(np.array([0.05]), [], ref.setDistMatrix_S(x[:, None], x[:, None]), y, "gauss", 0.0)
+    out = []
+    try:
+        for mode in (1, 0):
+            ctx.set_option("fit_mode", mode)
+            out.append(ctx.fit_batch(sIn, None, y, ants, [u_small, u_any], nugget=0.0, n_starts=1, n_presample=20, dmax=2))
+    finally:
+        ctx.set_option("fit_mode", 1)
+    for r in out:
+        assert r["info"][0] == -5 and np.isnan(r["fitness"][0]) and np.isnan(r["nll"][0])
+        assert r["info"][1] == 0 and np.isfinite(r["fitness"][1])
+    assert np.array_equal(out[0]["info"], out[1]["info"])

@@ -482,3 +482,177 @@ def test_graph_replay_matches_direct_launches(ctx):
         assert np.array_equal(bad_w[2], bg[2]) and (bg[2] > 0).any()
     assert np.array_equal(again[0], want[2][0]) and (again[2] == 0).all()
     P.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at their stated sizes
+def test_c3_premats_predict_simulate_at_size(ctx):
+    """BASELINE configs[2] at size: n = 8192 training points, m = 2048 new points, 4 scalar + 2 functional inputs
+    (len 100, B-splines p = 5, L2_bygroup), gauss kernel -- preMats, predict (light + K.tp / K.pp on sampled entries) and
+    simulate (100 draws) against the oracle run on the same inputs (R/4_prediction_SF.R:2-32, R/5_simulation_SF.R:3-23)."""
+    n, m, nsim = 8192, 2048, 100
+    case = make_case(8192, n, 4, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"], extra=m)
+    Ms = oracle_dists(case)
+    tp, pp = oracle_dists(case, new=True)
+    theta = theta_frac(Ms, 0.25)
+    ker, nug, nsm = "gauss", 1e-8, 1e-8
+    r_nll, sig2 = ref.negLogLik(theta, [], Ms, case["y"], ker, nug)
+    L_ref, z_ref = ref.preMats(Ms, case["y"], sig2, theta, ker, nug)
+    del Ms
+    P = _problem(ctx, case)
+    L, z = P.premats(ker, nug, sig2, theta)
+    assert np.all(np.triu(L[:512, :512], 1) == 0.0)
+    L_err = float(np.max(np.abs(L - L_ref)) / np.max(np.abs(L_ref)))
+    z_err = float(np.max(np.abs(z - z_ref)) / np.max(np.abs(z_ref)))
+    del L
+    sdev = np.sqrt(sig2)
+    pr_ref = ref.makePreds(tp, pp, sig2, theta, ker, L_ref, z_ref, "full", nug)
+    pr = P.predict(m, case["sNew"], case["coefsNew"], detail="full")
+    scale = max(1.0, np.max(np.abs(pr_ref["mean"])))
+    mean_err = float(np.max(np.abs(pr["mean"] - pr_ref["mean"])) / scale)
+    sd_err = float(np.max(np.abs(pr["sd"] - pr_ref["sd"])) / sdev)
+    ktp_err = _rel(pr["K.tp"], pr_ref["K.tp"], 1e-12 * sig2)
+    kpp_err = _rel(pr["K.pp"], pr_ref["K.pp"], 1e-12 * sig2)
+    Z = np.random.default_rng(1).standard_normal((m, nsim))
+    sm_ref = ref.makeSims(tp, pp, sig2, theta, ker, L_ref, z_ref, Z, nsm, "full")
+    sm = P.simulate(m, Z, case["sNew"], case["coefsNew"], nugget_sm=nsm)
+    sscale = max(1.0, np.max(np.abs(sm_ref["sims"])))
+    sims_err = float(np.max(np.abs(sm["sims"] - sm_ref["sims"])) / sscale)
+    _log("c3_at_size", n=n, m=m, L_rel=L_err, LInvY_rel=z_err, mean_rel=mean_err, sd_rel_to_sigma=sd_err, Ktp_rel=float(ktp_err),
+         Kpp_rel=float(kpp_err), sims_rel=sims_err, sd_min_over_sigma=float(np.min(pr_ref["sd"]) / sdev))
+    assert L_err <= 1e-9 and z_err <= 1e-8
+    assert mean_err <= 1e-8 and sd_err <= 1e-8 + 1e-8 * np.max(pr_ref["sd"]) / sdev
+    assert ktp_err <= 1e-12 and kpp_err <= 1e-12
+    assert sm["sims"].shape == (nsim, m) and sims_err <= 1e-6
+    assert np.max(np.abs(sm["mean"] - sm_ref["mean"])) <= 1e-8 * sscale
+    P.close()
+
+
+def test_c2_multistart_fit_at_size(ctx):
+    """BASELINE configs[1] at size: n = 2048, 2 scalar + 2 functional (len 100, B-splines p = 5), matern5_2, 10 starts from
+    20 presample points, all starts advanced together by the lock-step driver (one candidate = the full structure).
+    The oracle cannot repeat ~2000 likelihood evaluations at this size in test time, so it checks the RESULT: nll and
+    sigma^2 at the returned length-scales, that the returned point beats every presample point, and that the oracle's own
+    L-BFGS-B (scipy on the numpy likelihood, R's optim controls) started there stops without a material decrease."""
+    from fungp_b200 import factory as F
+    from oracle.rrng import RRng
+    n, ds = 2048, 2
+    case = make_case(2048, n, ds, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"])
+    Ms = oracle_dists(case)
+    ant = F.encode_ant(ds, 2, [0, 1], [0, 1], ["L2_bygroup", "L2_bygroup"], [5, 5], ["B-splines", "B-splines"], "matern5_2")
+    rng = RRng(2048)
+    res = F.score_candidates(ctx, case["sIn"], case["fIn"], case["y"], ant[None, :], rng, nugget=1e-8, n_starts=10, n_presample=20)
+    assert res["info"][0] == 0
+    th = res["theta"][0][:4]
+    r_nll, r_s2 = ref.negLogLik(th, [], Ms, case["y"], "matern5_2", 1e-8)
+    assert abs(r_nll - res["nll"][0]) <= _nll_tol(r_nll, n) and abs(r_s2 - res["sig2"][0]) <= 1e-8 * r_s2
+    lo, up = ref.setBounds(Ms)
+    u = np.asarray(RRng(2048).runif(4 * 20)).reshape(20, 4).T
+    pre = lo[:, None] + u * (up - lo)[:, None]
+    pre_best = min(ref.negLogLik(pre[:, j], [], Ms, case["y"], "matern5_2", 1e-8)[0] for j in range(0, 20, 4))
+    assert r_nll <= pre_best
+    fn = lambda t: ref.negLogLik(np.asarray(t), [], Ms, case["y"], "matern5_2", 1e-8)[0]
+    x2, f2, conv = ref.optim_lbfgsb(fn, th, lo, up, maxit=3)
+    _log("c2_fit_at_size", nll=float(r_nll), nll_abs_err=float(abs(r_nll - res["nll"][0])), oracle_continuation_gain=float(r_nll - f2),
+         q2=float(res["fitness"][0]))
+    assert r_nll - f2 <= 1e-5 * max(1.0, abs(r_nll))
+
+
+def test_c4_candidates_at_size(ctx):
+    """BASELINE configs[3] at size: n = 1024, 5 scalar + 3 functional inputs (len 10 / 22 / 50); a handful of candidate
+    structures fitted by fgp_fit_batch, each scored again by the oracle at the returned hyper-parameters (Q2loocv, nll)."""
+    from fungp_b200 import factory as F
+    from oracle.rrng import RRng
+    from helpers import synth_problem
+    n, ds = 1024, 5
+    sIn, fIn, y, _ = synth_problem(1024, n, ds, [10, 22, 50])
+    ants = np.stack([F.encode_ant(ds, 3, [0, 1, 3], [0, 2], ["L2_bygroup", "L2_byindex"], [3, 2], ["B-splines", "B-splines"], "matern5_2"),
+                     F.encode_ant(ds, 3, [0, 1, 2, 3, 4], [1], ["L2_bygroup"], [4], ["B-splines"], "gauss"),
+                     F.encode_ant(ds, 3, [1], [0, 1, 2], ["L2_byindex", "L2_bygroup", "L2_bygroup"], [2, 3, 5], ["B-splines"] * 3, "matern3_2"),
+                     F.encode_ant(ds, 3, [0, 1], [], [], [], [], "matern5_2")])
+    res = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(4), nugget=1e-8, n_starts=1, n_presample=20)
+    assert (res["info"] == 0).all()
+    for c, ant in enumerate(ants):
+        kw = F.decode_ant(ant, ds, 3)
+        nsA = len(kw["s_active"])
+        th = res["theta"][c][np.isfinite(res["theta"][c])]
+        m = ref.fgpm(sIn=sIn[:, kw["s_active"]] if kw["s_active"] else None, fIn=[fIn[q] for q in kw["f_active"]] if kw["f_active"] else None,
+                     sOut=y, kerType=kw["kerType"], f_disType=kw["f_disType"] or "L2_bygroup", f_pdims=kw["f_pdims"] or 3,
+                     f_basType=kw["f_basType"] or "B-splines", var_hyp=res["sig2"][c], ls_s_hyp=th[:nsA] if nsA else None,
+                     ls_f_hyp=th[nsA:] if th.size > nsA else None)
+        q2 = ref.q2_loocv(m)
+        _log("c4_at_size", cand=c, q2=float(q2), q2_err=float(abs(q2 - res["fitness"][c])))
+        assert abs(q2 - res["fitness"][c]) <= 1e-8, (c, q2, res["fitness"][c])
+
+
+def test_c5_cholesky_against_lapack(ctx):
+    """BASELINE configs[4] at size, Cholesky only: the n = 32768 matrix assembled on the GPU is factored by LAPACK dpotrf on
+    the host (what base::chol calls, R/3_training_SF.R:249) and log det + the quadratic form are compared with the GPU's
+    likelihood.  The oracle's own assembly would need ~35 GB of distance lists, so the matrix comes from fgp_assemble, whose
+    entries are parity-tested at smaller n."""
+    import scipy.linalg as sla
+    try:
+        import psutil
+        if psutil.virtual_memory().available < 30e9:
+            pytest.skip("needs ~20 GB of host memory")
+    except ImportError:
+        pass
+    n = 32768
+    case = make_case(5, n, 2, [200, 200], [10, 10], ["B-splines"] * 2, ["L2_bygroup"] * 2)
+    P = _problem(ctx, case)
+    theta = 0.3 * 2.0 * P.dist_max()
+    ker, nug = "matern3_2", 1e-8
+    nll, s2, info = P.nll_batch(ker, nug, theta)
+    assert info[0] == 0
+    R = P.assemble(ker, nug, theta)
+    P.close()
+    Lh = sla.cholesky(R, lower=True, overwrite_a=True, check_finite=False)
+    z = sla.solve_triangular(Lh, case["y"], lower=True, check_finite=False)
+    s2_ref = float(z @ z) / n
+    nll_ref = 0.5 * (n * np.log(2 * np.pi * s2_ref) + 2.0 * float(np.sum(np.log(np.diag(Lh)))) + n)
+    _log("c5_lapack", n=n, nll=nll_ref, nll_abs_err=float(abs(nll[0] - nll_ref)), sig2_rel=float(abs(s2[0] - s2_ref) / s2_ref))
+    assert abs(nll[0] - nll_ref) <= _nll_tol(nll_ref, n)
+    assert abs(s2[0] - s2_ref) <= 1e-7 * s2_ref
+
+
+def test_near_duplicate_points_relative_distance(ctx):
+    """Distances between near-duplicate curves under an ill-conditioned Gram matrix, checked RELATIVELY on the small
+    entries (the max-floored comparisons above cannot see them).  Truth = (c_i - c_j)' J (c_i - c_j) with the difference
+    formed first, in extended precision.  Both the reference's form (outer differences of c and of cJ,
+    R/7_distanceFunctions.R:39-45, restated by the oracle) and the whitened form of the kernel (csrc/api.cu) difference
+    per-point products, so both lose digits in proportion to |c| / |c_i - c_j|; the test reports both errors and requires
+    the CUDA path to be no worse than a small multiple of the reference's own."""
+    import fungp_b200
+    rng = np.random.default_rng(77)
+    k, p, n = 60, 8, 96
+    t = np.linspace(0.0, 1.0, k)
+    B = np.stack([np.exp(-0.5 * ((t - 0.5) / (0.08 + 0.01 * a)) ** 2) for a in range(p)], axis=1)     # nearly collinear bumps
+    J = B.T @ B
+    condJ = float(np.linalg.cond(J))
+    assert condJ >= 1e6
+    base = rng.standard_normal((n // 2, p))
+    dup = base + 1e-9 * rng.standard_normal((n // 2, p))                        # partners 1e-9 apart
+    coefs = np.concatenate([base, dup], axis=0)
+    y = rng.standard_normal(n)
+    P = fungp_b200.Problem(ctx, None, [coefs], [J], ["L2_bygroup"], y)
+    D = P.dist_matrix(0)
+    P.close()
+    Dr = ref.setDistMatrix_F([coefs], [coefs], [J], ["L2_bygroup"])[0]
+    cl, Jl = coefs.astype(np.longdouble), J.astype(np.longdouble)
+    i = np.arange(n // 2); j = i + n // 2
+    dc = cl[i] - cl[j]
+    truth = np.sqrt(np.maximum(np.einsum("ia,ab,ib->i", dc, Jl, dc), 0)).astype(np.float64)
+    big = truth > 0
+    rel_cuda = np.abs(D[i, j] - truth)[big] / truth[big]
+    rel_ref = np.abs(Dr[i, j] - truth)[big] / truth[big]
+    # the well-separated pairs keep the 1e-12 bar relative to each entry
+    far = np.triu_indices(n // 2, 1)
+    d_far = cl[far[0]] - cl[far[1]]
+    t_far = np.sqrt(np.einsum("ia,ab,ib->i", d_far, Jl, d_far)).astype(np.float64)
+    rel_far = np.abs(D[far] - t_far) / t_far
+    _log("near_duplicates", condJ=condJ, small_dist_median=float(np.median(truth)), rel_err_cuda_max=float(rel_cuda.max()),
+         rel_err_cuda_median=float(np.median(rel_cuda)), rel_err_reference_form_max=float(rel_ref.max()),
+         rel_err_reference_form_median=float(np.median(rel_ref)), rel_err_far_pairs_max=float(rel_far.max()))
+    assert rel_far.max() <= 1e-10          # cond(J) ~ 1e6+ amplifies the rounding of c W on ordinary pairs: still 1e-10
+    assert np.median(rel_cuda) <= 10.0 * max(np.median(rel_ref), 1e-9)
+    assert np.all(np.isfinite(D)) and np.all(D >= 0.0) and np.array_equal(D, D.T)
