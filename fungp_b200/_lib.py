@@ -34,6 +34,10 @@ SIGNATURES = {
     "fgp_assemble": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp, c_dp]),
     "fgp_nll_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, c_dp, c_dp, c_dp, c_dp, c_ip]),
     "fgp_premats": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp]),
+    "fgp_problem_restore": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp]),
+    "fgp_update_var": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp]),
+    "fgp_update_y": (C.c_int, [C.c_void_p, c_dp, c_dp]),
+    "fgp_premats_reuse": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, c_dp, c_ip]),
     "fgp_predict": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dpp, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "fgp_simulate": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dpp, C.c_int, c_dp, C.c_double, c_dp, c_dp, c_dp]),
     "fgp_loocv": (C.c_int, [C.c_void_p, c_dp, c_dp]),

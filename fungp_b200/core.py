@@ -255,6 +255,36 @@ class Problem:
         self.ctx.check(rc, "fgp_premats")
         return L, z
 
+    def restore(self, ker, nugget, sig2, theta, L, LInvY):
+        """re-create the device model from saved slots (preMats$L, preMats$LInvY) without factoring"""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        L = _f(L); z = np.ascontiguousarray(np.asarray(LInvY, dtype=np.float64).ravel())
+        assert L.shape == (self.n, self.n) and z.size == self.n
+        self.ctx.check(self.ctx.lib.fgp_problem_restore(self.h, KER[ker], float(nugget), float(sig2), _dp(theta), _dp(L), _dp(z)),
+                       "fgp_problem_restore")
+
+    def update_var(self, sig2_new, want_L=True):
+        L = np.zeros((self.n, self.n), order="F") if want_L else None
+        z = np.zeros(self.n)
+        self.ctx.check(self.ctx.lib.fgp_update_var(self.h, float(sig2_new), None if L is None else _dp(L), _dp(z)), "fgp_update_var")
+        return L, z
+
+    def update_y(self, y_new):
+        y = np.ascontiguousarray(np.asarray(y_new, dtype=np.float64).ravel())
+        z = np.zeros(self.n)
+        self.ctx.check(self.ctx.lib.fgp_update_y(self.h, _dp(y), _dp(z)), "fgp_update_y")
+        return z
+
+    def premats_reuse(self, old, want_L=True):
+        """model of this (updated) data set with the hyper-parameters of `old`, re-using old's factor for the leading
+        points both share -> (L, LInvY, n_reused)"""
+        L = np.zeros((self.n, self.n), order="F") if want_L else None
+        z = np.zeros(self.n)
+        nre = C.c_int()
+        self.ctx.check(self.ctx.lib.fgp_premats_reuse(self.h, old.h, None if L is None else _dp(L), _dp(z), C.byref(nre)),
+                       "fgp_premats_reuse")
+        return L, z, nre.value
+
     def _new(self, sNew, coefsNew, m):
         s = None if sNew is None else _f(np.asarray(sNew, dtype=np.float64).reshape(m, -1))
         cs = [_f(c) for c in (coefsNew or [])]

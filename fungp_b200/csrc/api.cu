@@ -387,6 +387,7 @@ extern "C" int fgp_problem_set_y(fgp_problem* P, const double* y) {
             CK(wait_stream(ctx, ctx->dev[s], ctx->dev[s].sPanel[0]));
         }
     P->hasModel = false;
+    P->loocvValid = false;
     return 0;
 }
 
@@ -436,7 +437,7 @@ extern "C" int fgp_dist_materialize(fgp_problem* P, int l, double* out) {
     return 0;
 }
 
-static AsmArgs train_asm(const fgp_problem* P, const ProblemDev& pd, int ker, const double* scale_dev) {
+AsmArgs fgp_train_asm(const fgp_problem* P, const ProblemDev& pd, int ker, const double* scale_dev) {
     AsmArgs a{};
     a.XP = pd.X; a.nP = P->n; a.ldP = P->n;
     a.XQ = pd.X; a.nQ = P->n; a.ldQ = P->n;
@@ -459,7 +460,7 @@ extern "C" int fgp_assemble(fgp_problem* P, int ker, double nugget, const double
     kernel_scales(ker, P->nterms, theta, sc.data());
     cudaStream_t st = d.sPanel[0];
     CK(cudaMemcpyAsync(d.small.p, sc.data(), sizeof(double) * P->nterms, cudaMemcpyHostToDevice, st));
-    AsmArgs a = train_asm(P, P->pd[0], ker, (const double*)d.small.p);
+    AsmArgs a = fgp_train_asm(P, P->pd[0], ker, (const double*)d.small.p);
     a.diag_rel = nugget; a.M = (double*)d.work.p; a.ld = n; a.strideM = 0; a.mirror = 1;
     launch_assemble(a, 1, st);
     CK(cudaGetLastError());
@@ -551,7 +552,7 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
                                cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(dInfo + g0, 0, sizeof(int) * gb, st));
             if (var_known) CK(cudaMemcpyAsync(dVar, &hVar, sizeof(double), cudaMemcpyHostToDevice, st));
-            AsmArgs a = train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
+            AsmArgs a = fgp_train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
             a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
             if (prof) d.timers.begin(st);
             launch_assemble(a, gb, st);
@@ -655,283 +656,3 @@ extern "C" int fgp_nll_batch(fgp_problem* P, int ker, double nugget, int B, cons
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ preMats
-extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, const double* theta, double* L_out,
-                           double* LInvY_out) {
-    if (!P || !theta || ker < 1 || ker > 3 || !(sig2 > 0.0)) return FGP_ERR_ARG;
-    fgp_ctx* ctx = P->ctx;
-    DevState& d = ctx->dev[0];
-    CK(cudaSetDevice(d.device));
-    ProblemDev& pd = P->pd[0];
-    const int n = P->n, nt = P->nterms;
-    const long ld = pick_ld(n + 1);
-    const int ncT = cdiv(n, FGP_TILE);
-    if (!pd.Lfac) {
-        pd.Lfac = (double*)d.pool.get(sizeof(double) * (size_t)ld * n);
-        pd.Wall = (double*)d.pool.get(sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE);
-        if (!pd.Lfac || !pd.Wall) { fgp_set_err(ctx, "fgp_premats: out of device memory"); return FGP_ERR_ALLOC; }
-        pd.ldL = ld;
-    }
-    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
-    std::vector<double> sc(nt);
-    kernel_scales(ker, nt, theta, sc.data());
-    cudaStream_t st = d.sPanel[0];
-    double* dScale = (double*)d.small.p;
-    int* dInfo = (int*)(dScale + nt);
-    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
-    AsmArgs a = train_asm(P, pd, ker, dScale);
-    a.mult = sig2; a.diag_rel = nugget; a.M = pd.Lfac; a.ld = ld; a.strideM = 0;
-    launch_assemble(a, 1, st);
-    launch_fill_yrow(pd.Lfac, ld, 0, 1, n, pd.y, n, st);
-    TrapDesc t{};
-    t.M = pd.Lfac; t.ld = ld; t.strideM = 0; t.batch = 1;
-    t.ncols = n; t.nrows = n + 1; t.holeLo = n + 1; t.holeHi = n + 1; t.colHoleLo = n; t.colHoleHi = n;
-    t.cpre = 0; t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
-    int rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
-    if (rc) return rc;
-    FGP_COUNT_WORK(2, 1);
-    int hinfo = 0;
-    CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(wait_stream(ctx, d, st));
-    CK(cudaGetLastError());
-    if (hinfo != 0) { P->hasModel = false; return hinfo; }
-    P->hasModel = true; P->ker = ker; P->nugget = nugget; P->sig2 = sig2;
-    P->theta.assign(theta, theta + nt);
-    if (LInvY_out)
-        CK(cudaMemcpy2D(LInvY_out, sizeof(double), pd.Lfac + n, sizeof(double) * ld, sizeof(double), n, cudaMemcpyDeviceToHost));
-    if (L_out) {
-        if (d.work.ensure(sizeof(double) * (size_t)n * n)) return FGP_ERR_ALLOC;
-        launch_extract_lower(pd.Lfac, ld, n, (double*)d.work.p, st);
-        CK(cudaMemcpyAsync(L_out, d.work.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
-        CK(wait_stream(ctx, d, st));
-    }
-    return 0;
-}
-
-// shared prologue of predict / simulate: workspace with L copied in, new-point coordinates uploaded
-struct NewPts {
-    double* Xnew = nullptr;   // m x ncoord on device
-};
-static int upload_new(fgp_problem* P, DevState& d, int m, const double* sNew, const double* const* coefsNew,
-                      double** Xnew_dev) {
-    fgp_ctx* ctx = P->ctx;
-    std::vector<double> X;
-    build_coords(P, m, sNew, coefsNew, X);
-    if (d.aux.ensure(sizeof(double) * std::max<size_t>(1, X.size()))) return FGP_ERR_ALLOC;
-    CK(cudaMemcpyAsync(d.aux.p, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice, d.sPanel[0]));
-    CK(wait_stream(ctx, d, d.sPanel[0]));
-    *Xnew_dev = (double*)d.aux.p;
-    return 0;
-}
-
-extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const double* const* coefsNew, int detail,
-                           double* mean, double* sd, double* Ktp, double* Kpp) {
-    if (!P || m <= 0 || !mean || !sd) return FGP_ERR_ARG;
-    fgp_ctx* ctx = P->ctx;
-    if (!P->hasModel) { fgp_set_err(ctx, "fgp_predict: call fgp_premats first"); return FGP_ERR_STATE; }
-    if ((P->ds > 0 && !sNew) || (P->df > 0 && !coefsNew)) return FGP_ERR_ARG;
-    DevState& d = ctx->dev[0];
-    CK(cudaSetDevice(d.device));
-    ProblemDev& pd = P->pd[0];
-    const int n = P->n, nt = P->nterms;
-    double* Xnew = nullptr;
-    int rc = upload_new(P, d, m, sNew, coefsNew, &Xnew);
-    if (rc) return rc;
-    const int holeHi = (int)roundup(n, FGP_TILE);
-    const int nrows = holeHi + m;
-    const long ld = pick_ld(nrows);
-    // workspace: trapezoid (ld x n) | results mean[m] norm[m]
-    const size_t trapBytes = sizeof(double) * (size_t)ld * n;
-    if (d.work.ensure(trapBytes + sizeof(double) * 2 * (size_t)m)) return FGP_ERR_ALLOC;
-    double* Mw = (double*)d.work.p;
-    double* dMean = (double*)((char*)d.work.p + trapBytes);
-    double* dNorm = dMean + m;
-    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
-    std::vector<double> sc(nt);
-    kernel_scales(P->ker, nt, P->theta.data(), sc.data());
-    cudaStream_t st = d.sPanel[0];
-    double* dScale = (double*)d.small.p;
-    int* dInfo = (int*)(dScale + nt);
-    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
-    // L -> top of the workspace
-    CK(cudaMemcpy2DAsync(Mw, sizeof(double) * ld, pd.Lfac, sizeof(double) * pd.ldL, sizeof(double) * n, n,
-                         cudaMemcpyDeviceToDevice, st));
-    // K(new, train) = sig2 * R(new, train) under it     (R/4_prediction_SF.R:6)
-    AsmArgs a{};
-    a.XP = Xnew; a.nP = m; a.ldP = m; a.XQ = pd.X; a.nQ = n; a.ldQ = n;
-    a.units = pd.units; a.nunits = (int)P->units.size(); a.scale = dScale; a.nterms = nt; a.ker = P->ker; a.sym = 0;
-    a.mult = P->sig2; a.M = Mw; a.ld = ld; a.strideM = 0; a.rowOff = holeHi; a.colOff = 0;
-    launch_assemble(a, 1, st);
-    TrapDesc t{};
-    t.M = Mw; t.ld = ld; t.strideM = 0; t.batch = 1;
-    t.ncols = n; t.nrows = nrows; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
-    t.cpre = cdiv(n, FGP_TILE); t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
-    rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
-    if (rc) return rc;
-    // mean = LInvK' LInvY ; sd = sqrt(pmax(sig2 - colSums(LInvK^2), 0))     (R/4_prediction_SF.R:10-11)
-    launch_rowstats(Mw, ld, 0, 1, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, 0, dNorm, dMean, st);
-    std::vector<double> hn(m);
-    CK(cudaMemcpyAsync(mean, dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    CK(wait_stream(ctx, d, st));
-    CK(cudaGetLastError());
-    for (int i = 0; i < m; ++i) sd[i] = sqrt(std::max(P->sig2 - hn[i], 0.0));
-    if (detail == FGP_DETAIL_FULL) {
-        if (Ktp) {   // n x m
-            if (d.work.ensure(sizeof(double) * (size_t)n * m)) return FGP_ERR_ALLOC;
-            AsmArgs b = a;
-            b.XP = pd.X; b.nP = n; b.ldP = n; b.XQ = Xnew; b.nQ = m; b.ldQ = m;
-            b.M = (double*)d.work.p; b.ld = n; b.rowOff = 0; b.colOff = 0;
-            launch_assemble(b, 1, st);
-            CK(cudaMemcpyAsync(Ktp, d.work.p, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToHost, st));
-            CK(wait_stream(ctx, d, st));
-        }
-        if (Kpp) {   // m x m, sig2 * (R_pp + nugget I)      (R/4_prediction_SF.R:16-17)
-            if (d.work.ensure(sizeof(double) * (size_t)m * m)) return FGP_ERR_ALLOC;
-            AsmArgs b = a;
-            b.XP = Xnew; b.nP = m; b.ldP = m; b.XQ = Xnew; b.nQ = m; b.ldQ = m; b.sym = 1; b.mirror = 1;
-            b.diag_rel = P->nugget; b.M = (double*)d.work.p; b.ld = m; b.rowOff = 0; b.colOff = 0;
-            launch_assemble(b, 1, st);
-            CK(cudaMemcpyAsync(Kpp, d.work.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost, st));
-            CK(wait_stream(ctx, d, st));
-        }
-        CK(cudaGetLastError());
-    }
-    return 0;
-}
-
-extern "C" int fgp_simulate(fgp_problem* P, int m, const double* sNew, const double* const* coefsNew, int nsim,
-                            const double* Z, double nugget_sm, double* sims, double* mean, double* sd) {
-    if (!P || m <= 0 || nsim <= 0 || !Z || !sims) return FGP_ERR_ARG;
-    fgp_ctx* ctx = P->ctx;
-    if (!P->hasModel) { fgp_set_err(ctx, "fgp_simulate: call fgp_premats first"); return FGP_ERR_STATE; }
-    if ((P->ds > 0 && !sNew) || (P->df > 0 && !coefsNew)) return FGP_ERR_ARG;
-    DevState& d = ctx->dev[0];
-    CK(cudaSetDevice(d.device));
-    ProblemDev& pd = P->pd[0];
-    const int n = P->n, nt = P->nterms;
-    double* Xnew = nullptr;
-    int rc = upload_new(P, d, m, sNew, coefsNew, &Xnew);
-    if (rc) return rc;
-    const int holeHi = (int)roundup(n, FGP_TILE);
-    const int nrows = holeHi + m, ncols = holeHi + m;
-    const long ld = pick_ld(nrows);
-    const size_t trapBytes = sizeof(double) * (size_t)ld * ncols;
-    const size_t extra = sizeof(double) * (2 * (size_t)m + (size_t)m * nsim * 2);
-    if (d.work.ensure(trapBytes + extra)) return FGP_ERR_ALLOC;
-    double* Mw = (double*)d.work.p;
-    double* dMean = (double*)((char*)d.work.p + trapBytes);
-    double* dNorm = dMean + m;
-    double* dZ = dNorm + m;
-    double* dSims = dZ + (size_t)m * nsim;
-    const int ncTall = cdiv(ncols, FGP_TILE), ncTA = cdiv(n, FGP_TILE);
-    if (d.wbuf.ensure(sizeof(double) * (size_t)ncTall * FGP_TILE * FGP_TILE)) return FGP_ERR_ALLOC;
-    double* Ww = (double*)d.wbuf.p;
-    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
-    std::vector<double> sc(nt);
-    kernel_scales(P->ker, nt, P->theta.data(), sc.data());
-    cudaStream_t st = d.sPanel[0];
-    double* dScale = (double*)d.small.p;
-    int* dInfo = (int*)(dScale + nt);
-    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
-    CK(cudaMemcpyAsync(dZ, Z, sizeof(double) * (size_t)m * nsim, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpy2DAsync(Mw, sizeof(double) * ld, pd.Lfac, sizeof(double) * pd.ldL, sizeof(double) * n, n,
-                         cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(Ww, pd.Wall, sizeof(double) * (size_t)ncTA * FGP_TILE * FGP_TILE, cudaMemcpyDeviceToDevice, st));
-    AsmArgs a{};
-    a.XP = Xnew; a.nP = m; a.ldP = m; a.XQ = pd.X; a.nQ = n; a.ldQ = n;
-    a.units = pd.units; a.nunits = (int)P->units.size(); a.scale = dScale; a.nterms = nt; a.ker = P->ker; a.sym = 0;
-    a.mult = P->sig2; a.M = Mw; a.ld = ld; a.strideM = 0; a.rowOff = holeHi; a.colOff = 0;
-    launch_assemble(a, 1, st);                       // K.ts'  (R/5_simulation_SF.R:8)
-    AsmArgs b = a;                                   // K.ss + nugget.sm I  (R/5_simulation_SF.R:9,14)
-    b.XQ = Xnew; b.nQ = m; b.ldQ = m; b.sym = 1; b.diag_abs = nugget_sm; b.colOff = holeHi;
-    launch_assemble(b, 1, st);
-    TrapDesc t{};
-    t.M = Mw; t.ld = ld; t.strideM = 0; t.batch = 1;
-    t.ncols = ncols; t.nrows = nrows; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = holeHi;
-    t.cpre = ncTA; t.upperRows = 0; t.W = Ww; t.strideW = 0; t.info = dInfo;
-    rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
-    if (rc) return rc;
-    launch_rowstats(Mw, ld, 0, 1, holeHi, m, n, 0, pd.Lfac + n, pd.ldL, 0, dNorm, dMean, st);
-    launch_lower_times(Mw + holeHi + (size_t)holeHi * ld, ld, m, dZ, nsim, dMean, dSims, st);
-    int hinfo = 0;
-    std::vector<double> hn(m), hm(m);
-    CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hm.data(), dMean, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hn.data(), dNorm, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(sims, dSims, sizeof(double) * (size_t)m * nsim, cudaMemcpyDeviceToHost, st));
-    CK(wait_stream(ctx, d, st));
-    CK(cudaGetLastError());
-    if (hinfo != 0) return hinfo;    // chol(K.ss - ...) failed: base R's error (quirk Q5)
-    if (mean) memcpy(mean, hm.data(), sizeof(double) * m);
-    if (sd) for (int i = 0; i < m; ++i) sd[i] = sqrt(std::max(P->sig2 - hn[i], 0.0));
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ LOOCV
-extern "C" int fgp_loocv(fgp_problem* P, double* y_pre, double* q2) {
-    if (!P || (!y_pre && !q2)) return FGP_ERR_ARG;
-    fgp_ctx* ctx = P->ctx;
-    if (!P->hasModel) { fgp_set_err(ctx, "fgp_loocv: call fgp_premats first"); return FGP_ERR_STATE; }
-    DevState& d = ctx->dev[0];
-    CK(cudaSetDevice(d.device));
-    ProblemDev& pd = P->pd[0];
-    const int n = P->n, nt = P->nterms;
-    const int holeHi = (int)roundup(n + 1, FGP_TILE);
-    const int nrows = holeHi + n;
-    const long ld = pick_ld(nrows);
-    const int ncT = cdiv(n, FGP_TILE);
-    const size_t trapBytes = sizeof(double) * (size_t)ld * n;
-    if (d.work.ensure(trapBytes + sizeof(double) * 2 * (size_t)n)) return FGP_ERR_ALLOC;
-    if (d.wbuf.ensure(sizeof(double) * (size_t)ncT * FGP_TILE * FGP_TILE)) return FGP_ERR_ALLOC;
-    if (d.small.ensure(sizeof(double) * nt + sizeof(int))) return FGP_ERR_ALLOC;
-    double* Mw = (double*)d.work.p;
-    double* dDiag = (double*)((char*)d.work.p + trapBytes);
-    double* dRy = dDiag + n;
-    std::vector<double> sc(nt);
-    kernel_scales(P->ker, nt, P->theta.data(), sc.data());
-    cudaStream_t st = d.sPanel[0];
-    double* dScale = (double*)d.small.p;
-    int* dInfo = (int*)(dScale + nt);
-    CK(cudaMemcpyAsync(dScale, sc.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(dInfo, 0, sizeof(int), st));
-    // R = tcrossprod(L)/sig2 + diag(nugget) = R0 + 2 nugget I  (quirk Q2, R/8_outilsStats.R:3)
-    AsmArgs a = train_asm(P, pd, P->ker, dScale);
-    a.diag_rel = 2.0 * P->nugget; a.M = Mw; a.ld = ld; a.strideM = 0;
-    launch_assemble(a, 1, st);
-    launch_fill_yrow(Mw, ld, 0, 1, n, pd.y, n, st);
-    launch_fill_identity_rows(Mw, ld, 0, 1, holeHi, n, st);
-    TrapDesc t{};
-    t.M = Mw; t.ld = ld; t.strideM = 0; t.batch = 1;
-    t.ncols = n; t.nrows = nrows; t.holeLo = n + 1; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
-    t.cpre = 0; t.upperRows = 1; t.W = (double*)d.wbuf.p; t.strideW = 0; t.info = dInfo;
-    int rc = trap_factor(ctx, 0, t, st, d.sBulk, false);
-    if (rc) return rc;
-    FGP_COUNT_WORK(1, 1);
-    // X = L^-T in the extra rows: diag(Rinv)_i = |X_i.|^2 ; (Rinv y)_i = X_i. (L^-1 y)
-    launch_rowstats(Mw, ld, 0, 1, holeHi, n, n, 1, Mw + n, ld, 0, dDiag, dRy, st);
-    std::vector<double> hd(n), hr(n);
-    int hinfo = 0;
-    CK(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hd.data(), dDiag, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hr.data(), dRy, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-    CK(wait_stream(ctx, d, st));
-    CK(cudaGetLastError());
-    if (hinfo != 0) return hinfo;
-    // y_pre = y - Rinv y / diag(Rinv)  (R/8_outilsStats.R:6);  Q2 = 1 - mean((y-yhat)^2)/mean((y-ybar)^2)
-    double ybar = 0.0;
-    for (int i = 0; i < n; ++i) ybar += P->y[i];
-    ybar /= n;
-    double se = 0.0, st2 = 0.0;
-    for (int i = 0; i < n; ++i) {
-        const double yh = P->y[i] - hr[i] / hd[i];
-        if (y_pre) y_pre[i] = yh;
-        se += (P->y[i] - yh) * (P->y[i] - yh);
-        st2 += (P->y[i] - ybar) * (P->y[i] - ybar);
-    }
-    if (q2) *q2 = 1.0 - (se / n) / (st2 / n);
-    return 0;
-}

@@ -339,6 +339,68 @@ __global__ void fill_identity_rows_kernel(double* M, long ld, long strideM, int 
         M[(long)blockIdx.z * strideM + (long)(row0 + i) + (long)j * ld] = (i == j) ? 1.0 : 0.0;
 }
 
+
+// zero the strict upper triangle of an m x m block (the factor of the conditional covariance becomes a dense operand)
+__global__ void zero_strict_upper_kernel(double* C, long ld, int m) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    for (int c = blockIdx.y + r + 1; c < m; c += gridDim.y) C[(long)r + (long)c * ld] = 0.0;
+}
+
+// out(s, i) = v[i] for all s < nrow   (sims start as the predictive mean, R/5_simulation_SF.R:15)
+__global__ void bcast_rows_kernel(double* out, long ld, int nrow, int ncol, const double* v) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)nrow * ncol) return;
+    const int s = (int)(idx % nrow), i = (int)(idx / nrow);
+    out[(long)s + (long)i * ld] = v[i];
+}
+
+// sigma^2-only update of a stored model: L <- a L (lower trapezoid), (L^-1 y)' <- (L^-1 y)' / a, inv(L_kk) <- inv(L_kk) / a
+__global__ void scale_factor_kernel(double* M, long ld, int n, double a, double ainv) {
+    const int j = blockIdx.y;                                  // column
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x) {
+        if (r < j) continue;
+        double* e = M + (long)r + (long)j * ld;
+        *e = (r == n) ? *e * ainv : *e * a;
+    }
+}
+__global__ void scale_vec_kernel(double* v, long count, double a) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) v[i] *= a;
+}
+
+__global__ void copy_row_kernel(double* M, long ld, int ncol, int src, int dst) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ncol) M[(long)dst + (long)j * ld] = M[(long)src + (long)j * ld];
+}
+
+// W_k = inv(L_kk) for every 128 x 128 diagonal block of a stored factor (restore of a saved model: the blocks the
+// panel solves of predict / simulate multiply with).  One CTA per block, thread c = column c by forward substitution;
+// a ragged last block is padded with the identity, as potf2_inv_kernel does.
+__global__ void __launch_bounds__(FGP_TILE) trtri_blocks_kernel(const double* M, long ld, int n, double* W) {
+    extern __shared__ double Ls[];         // [i][j], pitch 129
+    const int k0 = blockIdx.x * FGP_TILE, nb = min(FGP_TILE, n - k0), c = threadIdx.x;
+    for (int j = 0; j < FGP_TILE; ++j) {   // coalesced along rows
+        double v = (c == j) ? 1.0 : 0.0;
+        if (c < nb && j < nb && c >= j) v = M[(long)(k0 + c) + (long)(k0 + j) * ld];
+        Ls[c * 129 + j] = v;
+    }
+    __syncthreads();
+    // column c of inv(L): x_i = (delta_ic - sum_{j<i} L_ij x_j) / L_ii.  Every thread walks the same (i, j) range (its
+    // leading entries are zeros), so the L reads are broadcasts and the private x vector sits in coalesced local memory
+    double x[FGP_TILE];
+    for (int i = 0; i < FGP_TILE; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int j = 0; j < i; ++j) s = fma(-Ls[i * 129 + j], x[j], s);
+        x[i] = (i < c) ? 0.0 : s / Ls[i * 129 + i];
+    }
+    double* Wb = W + (long)blockIdx.x * FGP_TILE * FGP_TILE;
+    __syncthreads();
+    for (int i = 0; i < FGP_TILE; ++i) Ls[c * 129 + i] = x[i];                               // Ls[c][i] = X(i, c)
+    __syncthreads();
+    for (int col = 0; col < FGP_TILE; ++col) Wb[c + col * FGP_TILE] = Ls[col * 129 + c];     // W(r = c, col), coalesced
+}
+
 }  // namespace
 
 void launch_nll_reduce(const double* M, long ld, long strideM, int batch, int n, int yrow, const double* var_known,
@@ -389,4 +451,52 @@ void launch_fill_identity_rows(double* M, long ld, long strideM, int batch, int 
     dim3 grid(cdiv(n, 128), std::min(n, 65535), batch);
     FGP_COUNT_LAUNCH();
     fill_identity_rows_kernel<<<grid, 128, 0, st>>>(M, ld, strideM, row0, n);
+}
+
+void launch_zero_strict_upper(double* C, long ld, int m, cudaStream_t st) {
+    if (m <= 1) return;
+    FGP_COUNT_LAUNCH();
+    zero_strict_upper_kernel<<<dim3(cdiv(m, 128), std::min(m, 64)), 128, 0, st>>>(C, ld, m);
+}
+void launch_bcast_rows(double* out, long ld, int nrow, int ncol, const double* v, cudaStream_t st) {
+    const long tot = (long)nrow * ncol;
+    if (tot <= 0) return;
+    FGP_COUNT_LAUNCH();
+    bcast_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(out, ld, nrow, ncol, v);
+}
+void launch_scale_factor(double* M, long ld, int n, double* W, long wcount, double a, cudaStream_t st) {
+    FGP_COUNT_LAUNCH();
+    scale_factor_kernel<<<dim3(std::min(cdiv(n + 1, 256), 64), n), 256, 0, st>>>(M, ld, n, a, 1.0 / a);
+    FGP_COUNT_LAUNCH();
+    scale_vec_kernel<<<(unsigned)((wcount + 255) / 256), 256, 0, st>>>(W, wcount, 1.0 / a);
+}
+void launch_copy_row(double* M, long ld, int ncol, int src, int dst, cudaStream_t st) {
+    FGP_COUNT_LAUNCH();
+    copy_row_kernel<<<cdiv(ncol, 256), 256, 0, st>>>(M, ld, ncol, src, dst);
+}
+void launch_trtri_blocks(const double* M, long ld, int n, double* W, cudaStream_t st) {
+    static bool attr_set[FGP_MAXDEV] = {false};
+    const int smem = FGP_TILE * 129 * (int)sizeof(double);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < FGP_MAXDEV && !attr_set[dev]) {
+        cudaFuncSetAttribute(trtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set[dev] = true;
+    }
+    FGP_COUNT_LAUNCH();
+    trtri_blocks_kernel<<<cdiv(n, FGP_TILE), FGP_TILE, smem, st>>>(M, ld, n, W);
+}
+
+// C (rows x cols of 128-tiles, lower triangle only when `tri`) -= A B' over K columns: plain operands without holes.
+// rows / cols are the valid extents (ragged last tiles are masked).
+void launch_gemm_plain(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int rows, int cols, int K,
+                       bool tri, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.K = K; g.accumulate = 1; g.batch = 1;
+    if (tri) { g.tri0 = 0; g.triT = cdiv(rows, FGP_TILE); }
+    else { g.rectR0 = 0; g.rectNR = cdiv(rows, FGP_TILE); g.rectC0 = 0; g.rectNC = cdiv(cols, FGP_TILE); }
+    g.rowMin = 0; g.rowLo = rows; g.rowHoleHi = rows; g.nrows = rows;
+    g.colMin = 0; g.colLo = cols; g.colHoleHi = cols; g.ncols = cols;
+    launch_gemm(g, st);
 }

@@ -141,6 +141,13 @@ void launch_rowstats(const double* M, long ld, long strideM, int batch, int row0
                      const double* z, long zstride, long zbatch, double* norm, double* dot, cudaStream_t st);
 void launch_lower_times(const double* Lc, long ld, int m, const double* Z, int nsim, const double* mean, double* sims,
                         cudaStream_t st);
+void launch_zero_strict_upper(double* C, long ld, int m, cudaStream_t st);
+void launch_bcast_rows(double* out, long ld, int nrow, int ncol, const double* v, cudaStream_t st);
+void launch_scale_factor(double* M, long ld, int n, double* W, long wcount, double a, cudaStream_t st);
+void launch_copy_row(double* M, long ld, int ncol, int src, int dst, cudaStream_t st);
+void launch_trtri_blocks(const double* M, long ld, int n, double* W, cudaStream_t st);
+void launch_gemm_plain(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int rows, int cols, int K,
+                       bool tri, cudaStream_t st);
 void launch_extract_lower(const double* M, long ld, int n, double* out, cudaStream_t st);
 
 int fgp_peaks_device(double* dmma_tflops, double* dfma_tflops, double* copy_gbs);

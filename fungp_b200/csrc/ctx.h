@@ -170,9 +170,15 @@ struct fgp_problem {
     int ker = 0;
     double nugget = 0, sig2 = 0;
     std::vector<double> theta;
+    // leave-one-out predictions of the current model, kept for the callers that ask again (getFitness, then the
+    // calibration plot: R/7_plottingFunctions.R:9-11, 569-572 recompute solve(R) for the same model)
+    bool loocvValid = false;
+    std::vector<double> loocvY;
+    double loocvQ2 = 0.0;
 };
 
 int problem_upload(fgp_problem* P, int slot);
 // build the coordinate matrix rows for m points (host): scalars, byindex coefs, (c, cJ) pairs for bygroup
 void build_coords(const fgp_problem* P, int m, const double* sIn, const double* const* coefs, std::vector<double>& X);
 void kernel_scales(int ker, int nterms, const double* theta, double* scale);
+AsmArgs fgp_train_asm(const fgp_problem* P, const ProblemDev& pd, int ker, const double* scale_dev);

@@ -104,8 +104,11 @@ def optim_lbfgsb_batched(nll_batch, x0, lower, upper, maxit=100, factr=1e7, pgto
 
 def fgpm(sIn=None, fIn=None, sOut=None, kerType="matern5_2", f_disType="L2_bygroup", f_pdims=3, f_basType="B-splines",
          var_hyp=None, ls_s_hyp=None, ls_f_hyp=None, nugget=1e-8, n_starts=1, n_presample=20, rng=None, spoints_usr=None,
-         ctx=None, want_L=True):
-    """fgpm() (R/1_fgpm_Class.R:345-585): projection -> device problem -> setHypers_* -> preMats_*."""
+         ctx=None, want_L=True, reuse=None):
+    """fgpm() (R/1_fgpm_Class.R:345-585): projection -> device problem -> setHypers_* -> preMats_*.
+    reuse: a fitted model whose factor may be re-used (update() fast path): honoured when every hyper-parameter is given
+    and the length-scales, kernel and nugget are those of `reuse` -- the leading points both data sets share keep their
+    block of the factor (fgp_premats_reuse), a different variance is applied by rescaling (fgp_update_var)."""
     if sOut is None or (sIn is None and fIn is None):
         raise ValueError("fgpm: sOut and at least one of sIn / fIn are required")      # checkVal_fgpm
     if kerType not in KER:
@@ -214,6 +217,21 @@ def fgpm(sIn=None, fIn=None, sOut=None, kerType="matern5_2", f_disType="L2_bygro
             sig2 = float(var_hyp)
     m.kern.varHyp = sig2
     m.kern.s_lsHyps, m.kern.f_lsHyps = theta[:d_s].copy(), theta[d_s:].copy()
+    m.reused_points = 0
+    ro = None if reuse is None else getattr(reuse, "_problem", None)
+    if (ro is not None and ro.h and not s_free and not f_free and var_hyp is not None and reuse.kern.kerType == kerType
+            and reuse.nugget == nugget and ro.d == P.d and ro.ctx is ctx
+            and np.array_equal(np.r_[reuse.kern.s_lsHyps, reuse.kern.f_lsHyps], theta)):
+        try:
+            L, z, m.reused_points = P.premats_reuse(ro, want_L=want_L and sig2 == reuse.kern.varHyp)
+            if sig2 != reuse.kern.varHyp:
+                L, z = P.update_var(sig2, want_L=want_L)
+            m.preMats = dict(L=L, LInvY=z)
+            return m
+        except FgpError as e:
+            if isinstance(e, NotPosDefError):
+                raise
+            # structures differ (another projection dimension, distance or Gram matrix): plain preMats below
     L, z = P.premats(kerType, nugget, sig2, theta, want_L=want_L)  # preMats_*, R/4_prediction_SF.R:24-32
     m.preMats = dict(L=L, LInvY=z)
     return m
@@ -272,8 +290,10 @@ def loocv_q2(model):
 def update(model, sIn_nw=None, fIn_nw=None, sOut_nw=None, sIn_sb=None, fIn_sb=None, sOut_sb=None, ind_sb=None, ind_dl=None,
            var_sb=None, ls_s_sb=None, ls_f_sb=None, var_re=False, ls_s_re=False, ls_f_re=False, rng=None, ctx=None):
     """update.fgpm (R/1_fgpm_Class.R:1335-1506, R/6_updating.R): data deletion / substitution / addition, hyper-parameter
-    substitution or re-estimation.  As in the reference every branch ends in a fresh fgpm() call with the retained
-    hyper-parameters passed as known (R/6_updating.R:7-89, 91-323, 325-500, 502-565, 567-643); indices are 1-based."""
+    substitution or re-estimation.  As in the reference every branch ends in an fgpm() call with the retained
+    hyper-parameters passed as known (R/6_updating.R:7-89, 91-323, 325-500, 502-565, 567-643); indices are 1-based.
+    Where the length-scales are retained that call re-uses the model's factor (fgpm(reuse=model)): the points in front of
+    the first changed one keep their block, a new variance is a rescale -- instead of the reference's full refit."""
     sIn = None if model.sIn is None else model.sIn.copy()
     fIn = None if model.fIn is None else [f.copy() for f in model.fIn]
     y = model.sOut.copy()
@@ -306,4 +326,4 @@ def update(model, sIn_nw=None, fIn_nw=None, sOut_nw=None, sIn_sb=None, fIn_sb=No
     proj = model.f_proj
     return fgpm(sIn=sIn, fIn=fIn, sOut=y, kerType=k.kerType, f_disType=k.f_disType or "L2_bygroup",
                 f_pdims=proj.pdims if proj else 3, f_basType=proj.basType if proj else "B-splines", var_hyp=var, ls_s_hyp=ls_s,
-                ls_f_hyp=ls_f, nugget=model.nugget, rng=rng, ctx=ctx or model._ctx)
+                ls_f_hyp=ls_f, nugget=model.nugget, rng=rng, ctx=ctx or model._ctx, reuse=model)

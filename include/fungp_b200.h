@@ -94,9 +94,36 @@ int fgp_nll_batch(fgp_problem* prob, int ker, double nugget, int B, const double
 
 /* preMats_*: K = sig2*(R + nugget I), L = t(chol(K)), LInvY = L^-1 y  (R/4_prediction_SF.R:24-32).
  * L_out (n x n, explicit zeros above the diagonal) and LInvY_out (n) may be NULL; the factor always stays
- * resident on device 0 inside the problem for predict / simulate / loocv. */
+ * resident on device 0 inside the problem for predict / simulate / loocv, with `predict_reserve` (option, default 2048)
+ * free rows under it in which predict / simulate solve new points in place.  Large outputs (L_out here, K.tp / K.pp /
+ * sims below) travel in column chunks through pinned double buffers; L_out moves its lower triangle only. */
 int fgp_premats(fgp_problem* prob, int ker, double nugget, double sig2, const double* theta, double* L_out,
                 double* LInvY_out);
+
+/* (De)serialisation.  A saved fgpm object keeps preMats$L and preMats$LInvY in its slots but not the
+ * device handle (external pointers do not survive save()/load()): after load() the glue re-creates the problem from the
+ * slots (fgp_problem_create) and hands the stored factor back instead of assembling and factoring again.
+ * L is n x n column-major with zeros above the diagonal, exactly what fgp_premats returned; the inverses of the
+ * 128 x 128 diagonal blocks used by predict / simulate are rebuilt on the device (predictions agree with the
+ * pre-save model to rounding, ~1e-13 relative, not bit for bit).  Reference: the slots of R/1_fgpm_Class.R:65-84 and
+ * data/precalculated_Xfgpm_objects.rda, whose five models are restored this way in tests/. */
+int fgp_problem_restore(fgp_problem* prob, int ker, double nugget, double sig2, const double* theta, const double* L,
+                        const double* LInvY);
+
+/* update() fast paths (the reference refits with fgpm() in every branch of R/6_updating.R).
+ * fgp_update_var:  variance substitution (upd_subHypers, R/6_updating.R:510-524): L <- sqrt(s'/s) L, LInvY <- LInvY /
+ *                  sqrt(s'/s) on the stored factor; outputs as fgp_premats (may be NULL).
+ * fgp_update_y:    output substitution (upd_subData with sOut.sb only, R/6_updating.R:154-160): the factor is kept, only
+ *                  L^-1 y is solved again, O(n^2).
+ * fgp_premats_reuse: data addition / deletion / substitution with retained hyper-parameters (upd_add R/6_updating.R:325-500,
+ *                  upd_del :7-89, upd_subData :91-323).  prob_new holds the updated data set (fgp_problem_create), prob_old the
+ *                  fitted model.  The leading points both share (identical coordinates, same order), rounded down to a
+ *                  multiple of 128, keep their block of the factor; the rest is assembled and eliminated against it.
+ *                  n_reused (may be NULL) returns that count; 0 means a plain fgp_premats was done.  Result: the model of
+ *                  prob_new with prob_old's ker, nugget, sig2, theta -- what fgpm() with known hypers would give. */
+int fgp_update_var(fgp_problem* prob, double sig2_new, double* L_out, double* LInvY_out);
+int fgp_update_y(fgp_problem* prob, const double* y_new, double* LInvY_out);
+int fgp_premats_reuse(fgp_problem* prob_new, const fgp_problem* prob_old, double* L_out, double* LInvY_out, int* n_reused);
 
 /* makePreds_*: (R/4_prediction_SF.R:2-21).  sNew m x ds, coefsNew[i] m x p[i] (already projected).
  * mean[m], sd[m]; detail = full additionally fills Ktp (n x m) and Kpp (m x m) when non-NULL. */
@@ -109,7 +136,9 @@ int fgp_simulate(fgp_problem* prob, int m, const double* sNew, const double* con
                  const double* Z, double nugget_sm, double* sims, double* mean, double* sd);
 
 /* getOut_loocv + Q2 (R/8_outilsStats.R:1-7, R/1_Xfgpm_Class.R:522-543), including quirk Q2 (nugget counted twice).
- * y_pre[n] (may be NULL), q2 scalar. */
+ * y_pre[n] (may be NULL), q2 scalar.  The result is kept with the model: asking again (getFitness, then the calibration
+ * plot, R/7_plottingFunctions.R:9-11, 569-572, which recompute solve(R) for the same model) costs nothing until the
+ * model changes. */
 int fgp_loocv(fgp_problem* prob, double* y_pre, double* q2);
 
 /* ---- batched candidate scoring for the ant-colony search ------------------------------------------ */
@@ -125,8 +154,15 @@ int fgp_loocv(fgp_problem* prob, double* y_pre, double* q2);
  * with ndeps 1e-3 clipped at the box, as stats::optim does) -> preMats -> Q2loocv.
  * Outputs per candidate: fitness (Q2, NaN on crash), nll, sig2, theta (dmax per candidate, NaN padded), info (0, the
  * failing minor's order, or < 0: -1 bad structure, -4 more than dmax length-scales, -5 every start crashed).
- * Candidates are dealt from a host-side queue to `fit_workers` (option, default 4) worker threads per GPU of the
- * context, each with its own streams and workspaces; GPUs exchange nothing. */
+ * Scheduling (option "fit_mode"): 1 (default) = lock-step -- ONE host thread per GPU of the context advances all
+ * in-flight candidates together; every round the pending likelihood points of all of them (presample points,
+ * finite-difference points of an L-BFGS-B iterate, the value at the optimum) form one heterogeneous batched launch
+ * sequence, and the leave-one-out factorisations of the candidates that finished are batched the same way; options
+ * "fit_points" (points per round and lane, default 512 or what memory allows) and "fit_lanes" (rounds in flight per GPU).
+ * 0 = one host thread per candidate, `fit_workers` (option, default 8) of them per GPU, each with its own streams and
+ * workspaces.  Per-item results do not depend on the mode, the options or the number of GPUs; GPUs exchange nothing.
+ * A failure of the library itself (CUDA error, out of memory) is returned as the call's error code, not reported as
+ * crashed candidates. */
 int fgp_fit_batch(fgp_ctx* ctx, int n, int ds, const double* sIn, int df, const int* k, const double* const* fIn,
                   const double* y, int n_cand, const int* ants, double nugget, int n_starts, int n_presample,
                   const double* u01, const long long* u01_off, int dmax, double* fitness, double* nll, double* sig2,
@@ -161,7 +197,8 @@ int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
  * "outer" (column tiles of 128 per outer panel; the trailing update runs with K = outer*128), "outer_single" (the same for the look-ahead
  * path of a single factorisation; 0 = chosen by size: 2 below n = 12288, 8 below 24576, else 16), "fit_workers" (1..16),
  * "fit_blocking" (host waits of the fgp_fit_batch worker contexts: 0 spin, 1 sleep on a blocking event, 2 poll and yield;
- * default -1 = yield when workers x visible GPUs exceed 3/4 of the host cores, else spin),
+ * default -1 = yield when workers x visible GPUs exceed 3/4 of the host cores, else spin; the lock-step driver spins unless > 0),
+ * "fit_mode", "fit_points", "fit_lanes" (see fgp_fit_batch), "predict_reserve" (rows kept free under a stored factor),
  * "blocking_sync" (0/1/2, default 0: the same for this context's own calls),
  * "graphs" (0/1, default 0: batched likelihood calls at n < 2048 are captured as a CUDA graph the second time a shape is
  * seen on a problem and replayed afterwards -- one driver call per evaluation batch instead of ~30). */

@@ -99,3 +99,155 @@ def test_fit_predict_simulate_update_vs_oracle(ctx, ker, n_starts):
     assert abs(gd.kern.varHyp - od.varHyp) <= 1e-7 * od.varHyp
     for mm in (g, gu, gd):
         mm.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# update() fast paths, (f4): restore of a saved model, LOOCV cache
+def _known_fit(ref_kw, sIn, fIn, y, g):
+    return ref.fgpm(sIn=sIn, fIn=fIn, sOut=y, var_hyp=g.kern.varHyp, ls_s_hyp=g.kern.s_lsHyps, ls_f_hyp=g.kern.f_lsHyps, nugget=1e-8, **ref_kw)
+
+
+@pytest.mark.parametrize("n", [300, 2048])
+def test_update_fast_paths_vs_oracle_refit(ctx, n):
+    """add / delete / substitute points, substitute outputs, substitute the variance -- each against a FRESH oracle fit of
+    the updated data set with the retained hyper-parameters (what R/6_updating.R does by calling fgpm() again)."""
+    from fungp_b200 import model as M
+    m_new = 70
+    sIn, fIn, y, _ = synth_problem(79, n, 2, [30, 40], extra=m_new)
+    tr, te = slice(0, n), slice(n, n + m_new)
+    skw = dict(kerType="matern5_2", f_disType=["L2_bygroup", "L2_byindex"], f_pdims=[4, 2], f_basType=["B-splines", "B-splines"])
+    g = M.fgpm(sIn=sIn[tr], fIn=[f[tr] for f in fIn], sOut=y[tr], rng=RRng(5), ctx=ctx, nugget=1e-8, n_starts=1, n_presample=20, **skw)
+
+    def check(gm, osIn, ofIn, oy, what, min_reuse):
+        o = _known_fit(skw, osIn, ofIn, oy, gm)
+        Lg, Lo = gm.preMats["L"], o.L
+        assert Lg.shape == Lo.shape, what
+        assert np.max(np.abs(Lg - Lo)) <= 1e-9 * np.max(np.abs(Lo)), what
+        assert np.all(np.triu(Lg, 1) == 0.0), what
+        assert np.max(np.abs(gm.preMats["LInvY"] - o.LInvY)) <= 1e-8 * np.max(np.abs(o.LInvY)), what
+        assert gm.reused_points >= min_reuse, (what, gm.reused_points)
+        pg = M.predict(gm, sIn_pr=sIn[te][:9], fIn_pr=[f[te][:9] for f in fIn])
+        po = ref.predict(o, sNew=sIn[te][:9], fNew=[f[te][:9] for f in fIn])
+        assert np.max(np.abs(pg["mean"] - po["mean"])) <= 1e-8 * max(1.0, np.max(np.abs(po["mean"]))), what
+        assert np.max(np.abs(pg["sd"] - po["sd"])) <= 1e-8 * np.sqrt(gm.kern.varHyp) + 1e-8 * np.max(po["sd"]), what
+
+    full = (n // 128) * 128
+    # addition of 64 points: everything the old model factored in whole tiles is kept
+    ga = M.update(g, sIn_nw=sIn[n:n + 64], fIn_nw=[f[n:n + 64] for f in fIn], sOut_nw=y[n:n + 64])
+    check(ga, sIn[:n + 64], [f[:n + 64] for f in fIn], y[:n + 64], "add", full)
+    # deletion of three late points (1-based indices): the points in front of the first one are kept
+    dl = np.array([n - 40, n - 17, n - 3])
+    keep = np.setdiff1d(np.arange(n), dl - 1)
+    gd = M.update(g, ind_dl=dl)
+    check(gd, sIn[keep], [f[keep] for f in fIn], y[keep], "delete", ((n - 41) // 128) * 128)
+    # substitution of two input points and their outputs
+    sb = np.array([n - 20, n - 5])
+    s2 = sIn[tr].copy(); f2 = [f[tr].copy() for f in fIn]; y2 = y[tr].copy()
+    s2[sb - 1] = sIn[n + 64:n + 66]; y2[sb - 1] = y[n + 64:n + 66]
+    for q in range(2):
+        f2[q][sb - 1] = fIn[q][n + 64:n + 66]
+    gs = M.update(g, sIn_sb=s2[sb - 1], fIn_sb=[f[sb - 1] for f in f2], sOut_sb=y2[sb - 1], ind_sb=sb)
+    check(gs, s2, f2, y2, "substitute", ((n - 21) // 128) * 128)
+    # output substitution only, and variance substitution only: the whole factor is kept
+    y3 = y[tr].copy(); y3[[3, 10]] += 0.5
+    gy = M.update(g, sOut_sb=y3[[3, 10]], ind_sb=[4, 11])
+    check(gy, sIn[tr], [f[tr] for f in fIn], y3, "outputs", full)
+    gv = M.update(g, var_sb=1.7 * g.kern.varHyp)
+    assert gv.kern.varHyp == 1.7 * g.kern.varHyp
+    check(gv, sIn[tr], [f[tr] for f in fIn], y[tr], "variance", full)
+    # in-place entry points of the C ABI: fgp_update_y / fgp_update_var on the model's own handle
+    z3 = g._problem.update_y(y3)
+    assert np.max(np.abs(z3 - gy.preMats["LInvY"])) <= 1e-10 * np.max(np.abs(z3))
+    Lv, zv = g._problem.update_var(1.7 * g.kern.varHyp)
+    assert np.max(np.abs(Lv - gv.preMats["L"])) <= 1e-12 * np.max(np.abs(Lv))
+    assert np.max(np.abs(zv * np.sqrt(1.7) - z3)) <= 1e-10 * np.max(np.abs(z3))
+    for mm in (g, ga, gd, gs, gy, gv):
+        mm.close()
+
+
+def test_append_is_much_cheaper_than_a_refit(ctx):
+    """n = 8192, 64 points added with retained hyper-parameters: the fast path factors 64 + (n mod 128) columns against the
+    stored factor; a refit factors all of them.  Same L to 1e-9; at least 10x faster."""
+    import time
+    import fungp_b200
+    from helpers import make_case
+    n, k = 8192, 64
+    case = make_case(8192, n + k, 4, [100, 100], [5, 5], ["B-splines", "B-splines"], ["L2_bygroup", "L2_bygroup"])
+    sl = lambda a, m: None if a is None else a[:m]
+    P0 = fungp_b200.Problem(ctx, sl(case["sIn"], n), [c[:n] for c in case["coefs"]], case["J"], case["dis"], case["y"][:n])
+    theta = 0.25 * 2.0 * P0.dist_max()
+    _, s2, info = P0.nll_batch("gauss", 1e-8, theta)
+    assert info[0] == 0
+    P0.premats("gauss", 1e-8, s2[0], theta, want_L=False)
+    P1 = fungp_b200.Problem(ctx, case["sIn"], case["coefs"], case["J"], case["dis"], case["y"])
+    P2 = fungp_b200.Problem(ctx, case["sIn"], case["coefs"], case["J"], case["dis"], case["y"])
+    for _ in range(2):
+        t0 = time.perf_counter(); _, z1, nre = P1.premats_reuse(P0, want_L=False); t_fast = time.perf_counter() - t0
+        t0 = time.perf_counter(); _, z2 = P2.premats("gauss", 1e-8, s2[0], theta, want_L=False); t_full = time.perf_counter() - t0
+    assert nre == n
+    assert np.max(np.abs(z1 - z2)) <= 1e-8 * np.max(np.abs(z2))
+    L1, _, _ = P1.premats_reuse(P0)
+    L2, _ = P2.premats("gauss", 1e-8, s2[0], theta)
+    assert np.max(np.abs(L1 - L2)) <= 1e-9 * np.max(np.abs(L2))
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_log.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test="append_64_at_8192", fast_ms=t_fast * 1e3, refit_ms=t_full * 1e3, speedup=t_full / t_fast)) + "\n")
+    assert t_full >= 10.0 * t_fast, (t_fast, t_full)
+    for P in (P0, P1, P2):
+        P.close()
+
+
+def test_saved_model_restores_and_predicts_identically(ctx):
+    """save() / load() of a fitted model keeps the slots, not the device handle: a new problem is created from the stored
+    data and the stored preMats are handed back (fgp_problem_restore) -- no assembly, no factorisation.  The restored
+    model predicts, simulates and cross-validates like the original; so do the reference's own five stored models
+    (data/precalculated_Xfgpm_objects.rda) against the oracle's predictions from the stored L / LInvY."""
+    import fungp_b200
+    from fungp_b200 import model as M
+    from helpers import load_models
+    n, m = 700, 90
+    sIn, fIn, y, _ = synth_problem(83, n, 2, [30, 40], extra=m)
+    tr, te = slice(0, n), slice(n, n + m)
+    g = M.fgpm(sIn=sIn[tr], fIn=[f[tr] for f in fIn], sOut=y[tr], kerType="matern5_2", f_disType=["L2_bygroup", "L2_byindex"],
+               f_pdims=[4, 2], f_basType=["B-splines", "PCA"], rng=RRng(5), ctx=ctx)
+    theta = np.r_[g.kern.s_lsHyps, g.kern.f_lsHyps]
+    Z = RRng(1).rnorm(m * 4).reshape((4, m)).T
+    p0 = M.predict(g, sIn_pr=sIn[te], fIn_pr=[f[te] for f in fIn])
+    s0 = M.simulate(g, nsim=4, sIn_sm=sIn[te], fIn_sm=[f[te] for f in fIn], nugget_sm=1e-8, Z=Z)
+    q0 = M.loocv_q2(g)
+    assert M.loocv_q2(g) == q0                                      # second request: served from the model's cache
+    # "load": nothing but the slots -- data, projection, hyper-parameters, preMats
+    w0 = ctx.work_count(2)
+    P = fungp_b200.Problem(ctx, g.sIn, g.f_proj.coefs, g.f_proj.J, g.kern.f_disType, g.sOut)
+    P.restore("matern5_2", g.nugget, g.kern.varHyp, theta, g.preMats["L"], g.preMats["LInvY"])
+    assert ctx.work_count(2) == w0                                  # no preMats factorisation happened
+    cn = [ctx.project(f[te], p, B=B)[2] for f, p, B in zip(fIn, g.f_proj.pdims, g.f_proj.basis)]
+    p1 = P.predict(m, sIn[te], cn)
+    s1 = P.simulate(m, Z, sIn[te], cn, nugget_sm=1e-8)
+    assert np.max(np.abs(p1["mean"] - p0["mean"])) <= 1e-11 * max(1.0, np.max(np.abs(p0["mean"])))
+    assert np.max(np.abs(p1["sd"] - p0["sd"])) <= 1e-10 * np.sqrt(g.kern.varHyp)
+    assert np.max(np.abs(s1["sims"] - s0)) <= 1e-7 * max(1.0, np.max(np.abs(s0)))
+    assert abs(P.loocv()[1] - q0) <= 1e-12
+    P.close(); g.close()
+    # the reference's stored models: restore from the rda's L / LInvY, predict at the training inputs + a shift
+    for name, gm in load_models().items():
+        kw = dict(sIn=gm.get("sIn") if gm["ds"] else None)
+        coefs, J, dis = [], [], []
+        if gm["df"]:
+            bcj = ref.dimReduction(gm["fIn"], gm["f_pdims"], gm["f_basType"])
+            coefs, J, dis = bcj["coefs"], bcj["J"], gm["f_disType"]
+        Pm = fungp_b200.Problem(ctx, kw["sIn"], coefs, J, dis, gm["sOut"])
+        th = np.concatenate([gm["s_ls"], gm["f_ls"]])
+        Pm.restore(gm["kerType"], gm["nugget"], gm["varHyp"], th, gm["L"], gm["LInvY"])
+        nn = gm["sOut"].size
+        sN = None if not gm["ds"] else gm["sIn"] + 0.013
+        cN = [c + 0.02 for c in coefs]
+        pr = Pm.predict(nn, sN, cN)
+        tp = (ref.setDistMatrix_S(gm["sIn"], sN) if gm["ds"] else []) + (ref.setDistMatrix_F(coefs, cN, J, dis) if gm["df"] else [])
+        po = ref.makePreds(tp, None, gm["varHyp"], th, gm["kerType"], gm["L"], gm["LInvY"], "light", gm["nugget"])
+        assert np.max(np.abs(pr["mean"] - po["mean"])) <= 1e-8 * max(1.0, np.max(np.abs(po["mean"]))), name
+        assert np.max(np.abs(pr["sd"] - po["sd"])) <= 1e-8 * np.sqrt(gm["varHyp"]) + 1e-8 * np.max(po["sd"]), name
+        assert abs(Pm.loocv()[1] - gm["fitness"]) <= 1e-8, name
+        Pm.close()
