@@ -137,8 +137,10 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "graphs")) ctx->graphs = value != 0;
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "fit_mode")) ctx->fit_mode = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "pdl")) ctx->pdl = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "fused_assembly")) ctx->fused_assembly = value != 0 ? 1 : 0;
     else if (!strcmp(name, "fit_points")) ctx->fit_points = std::max(0, std::min((int)value, 4096));
-    else if (!strcmp(name, "fit_lanes")) ctx->fit_lanes = std::max(0, std::min((int)value, 2));
+    else if (!strcmp(name, "fit_lanes")) ctx->fit_lanes = std::max(0, std::min((int)value, 4));
     else if (!strcmp(name, "predict_reserve")) ctx->predict_reserve = std::max(128, std::min((int)value, 1 << 20));
     else if (!strcmp(name, "outer")) ctx->outer = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "outer_single")) ctx->outer_single = std::max(0, std::min((int)value, 16));
@@ -555,7 +557,9 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             AsmArgs a = fgp_train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
             a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
             if (prof) d.timers.begin(st);
-            launch_assemble(a, gb, st);
+            // the points of a batch share every coordinate difference: one batch-fused launch (bit-identical entries)
+            if (gb >= 2 && ctx->fused_assembly && assemble_fusable(nt, (int)P->units.size())) launch_assemble_fused(a, nullptr, 1, gb, st);
+            else launch_assemble(a, gb, st);
             if (prof) d.timers.end(st, FgpTimers::ASSEMBLY, 0.0);
             launch_fill_yrow(Mg, ld, (long)ld * n, gb, n, pd.y, n, st);
             TrapDesc t{};

@@ -148,12 +148,14 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                         const double d = fabs(xp[i] - xq[j]);
                         if (KER == 0) S[i][j] = d;
                         else {
-                            const double av = d * sc;
+                            // explicit roundings (no contraction left to the compiler): assemble_fused_kernel repeats these
+                            // operations one for one and must give the same bits
+                            const double av = __dmul_rn(d, sc);
                             if (KER == 1) S[i][j] = fma(av, av, S[i][j]);
                             else {
-                                S[i][j] += av;
-                                if (KER == 2) Pr[i][j] *= fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0);
-                                else Pr[i][j] *= (1.0 + av);
+                                S[i][j] = __dadd_rn(S[i][j], av);
+                                if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
+                                else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
                             }
                         }
                     }
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                         D2[i][j] = fma(d, d, D2[i][j]);
                     }
                 if (flag & 2) {
-                    const double sc2 = sc * sc;
+                    const double sc2 = __dmul_rn(sc, sc);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -177,10 +179,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                             if (KER == 0) S[i][j] = sqrt(d2);
                             else if (KER == 1) S[i][j] = fma(d2, sc2, S[i][j]);
                             else {
-                                const double av = sqrt(d2) * sc;
-                                S[i][j] += av;
-                                if (KER == 2) Pr[i][j] *= fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0);
-                                else Pr[i][j] *= (1.0 + av);
+                                const double av = __dmul_rn(sqrt(d2), sc);
+                                S[i][j] = __dadd_rn(S[i][j], av);
+                                if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
+                                else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
                             }
                         }
                 }
@@ -219,11 +221,11 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
         for (int i = 0; i < 4; ++i) {
             double r;
             if (KER == 0) r = S[i][j];
-            else if (KER == 1) r = exp_nonpos(-0.5 * S[i][j]);
-            else r = Pr[i][j] * exp_nonpos(-S[i][j]);
+            else if (KER == 1) r = exp_nonpos(__dmul_rn(-0.5, S[i][j]));
+            else r = __dmul_rn(Pr[i][j], exp_nonpos(-S[i][j]));
             if (KER != 0) {
-                if (diagTile && lr[i] == lc0 + j) r = a.mult * (r + a.diag_rel) + a.diag_abs;
-                else if (scaled) r *= a.mult;
+                if (diagTile && lr[i] == lc0 + j) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
+                else if (scaled) r = __dmul_rn(r, a.mult);
             }
             v[i] = r;
         }
@@ -243,6 +245,188 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
             for (int i = 0; i < 4; ++i) {
                 const int gi = i0 + lr[i];
                 if (gi < a.nP) M[(long)(a.colOff + gi) * a.ld + a.rowOff + gj] = v[i];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch-fused variant.  The B points of one finite-difference gradient (theta, theta +- 1e-3 e_i), of a presample or of a
+// multistart share every coordinate difference -- only the length-scales differ -- so a tile computes the per-term base
+// quantities ONCE (|x_i - x_j| of an index unit; the summed squares, or their root for the Matern kernels, of a group
+// term) and then runs B times over (scale, accumulate, exp, store).  Per matrix and entry that leaves 1-2 FP64
+// instructions per term + the 18 of the exp instead of 2-3 per coordinate + 18: the kernel moves from the FP64-issue
+// ceiling towards the HBM write roofline.  The arithmetic per entry is instruction for instruction that of
+// assemble_kernel (same operations in the same order), so both kernels produce bit-identical matrices.
+// Tile 64 rows x 32 columns, 256 threads, 4 x 2 entries per thread (the base quantities of 8 entries x up to 8 terms
+// live in registers); structures with more than 8 length-scales or 48 units use assemble_kernel.
+constexpr int FR = 64, FC = 32;          // fused tile
+constexpr int FCC = 48;                  // units (coordinate columns) a fused tile can stage
+constexpr int FNT = 8;                   // length-scale terms
+constexpr int FBCH = 32;                 // batch elements whose multipliers are staged at a time
+
+struct FusedK {
+    AsmArgs a;
+    const AsmGroup* groups;   // null: one group = elements [0, count)
+    int count;
+};
+
+template <int KER>
+__global__ void __launch_bounds__(ATHREADS, 1) assemble_fused_kernel(FusedK k) {
+    __shared__ __align__(16) double sP[FCC][FR];
+    __shared__ __align__(16) double sQ[FCC][FC];
+    __shared__ double sSc[FBCH][FNT], sSc2[FBCH][FNT];
+    __shared__ int sCol[FCC], sFlag[FCC], sTermFirst[FNT + 1], sNterms;
+    const AsmArgs& a = k.a;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;             // rows 4tx..4tx+3, columns 2ty, 2ty+1
+    // tile (I over 64-row blocks, J over 32-column blocks) with J <= 2I + 1: t = I (I + 1) + J
+    int I = (int)((sqrtf(4.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
+    while ((I + 1) * (I + 2) <= (int)blockIdx.x) ++I;
+    while (I * (I + 1) > (int)blockIdx.x) --I;
+    const int J = blockIdx.x - I * (I + 1);
+    const int i0 = I * FR, j0 = J * FC;
+    AsmGroup g;
+    if (k.groups) g = k.groups[blockIdx.y];
+    else { g.first = 0; g.count = k.count; }
+    const double* X = a.XP;
+    const FgpUnit* units = a.units;
+    int nunits = a.nunits;
+    if (a.elems) { const AsmElem e = a.elems[g.first]; X = e.X; units = e.units; nunits = e.nunits; }
+    if (tid < nunits) {
+        const FgpUnit un = units[tid];
+        sCol[tid] = un.col;
+        sFlag[tid] = (un.kind ? 1 : 0) | (un.last ? 2 : 0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        sTermFirst[0] = 0;
+        for (int u = 0; u < nunits; ++u)
+            if (sFlag[u] & 2) sTermFirst[++t] = u + 1;
+        sNterms = t;
+    }
+    for (int idx = tid; idx < nunits * FR; idx += ATHREADS) {
+        const int c = idx / FR, pnt = idx % FR;
+        sP[c][pnt] = (i0 + pnt < a.nP) ? X[(long)sCol[c] * a.ldP + i0 + pnt] : 0.0;
+    }
+    for (int idx = tid; idx < nunits * FC; idx += ATHREADS) {
+        const int c = idx / FC, pnt = idx % FC;
+        sQ[c][pnt] = (j0 + pnt < a.nQ) ? X[(long)sCol[c] * a.ldQ + j0 + pnt] : 0.0;
+    }
+    __syncthreads();
+    const int nterms = sNterms;
+
+    // ---- base quantity of every term: |x_i - x_j|, or the summed squares (gauss) / their root (Matern) of a group
+    double q[4][2][FNT];
+    unsigned groupMask = 0;
+#pragma unroll
+    for (int t = 0; t < FNT; ++t) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q[i][0][t] = 0.0; q[i][1][t] = 0.0; }
+        if (t < nterms) {
+            const int u0 = sTermFirst[t], u1 = sTermFirst[t + 1];
+            if (!(sFlag[u0] & 1)) {
+                const double2 p01 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx]);
+                const double2 p23 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx + 2]);
+                const double2 qq = *reinterpret_cast<const double2*>(&sQ[u0][2 * ty]);
+                const double xp[4] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { q[i][0][t] = fabs(xp[i] - qq.x); q[i][1][t] = fabs(xp[i] - qq.y); }
+            } else {
+                groupMask |= 1u << t;
+                double D2[4][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { D2[i][0] = 0.0; D2[i][1] = 0.0; }
+                for (int u = u0; u < u1; ++u) {
+                    const double2 p01 = *reinterpret_cast<const double2*>(&sP[u][4 * tx]);
+                    const double2 p23 = *reinterpret_cast<const double2*>(&sP[u][4 * tx + 2]);
+                    const double2 qq = *reinterpret_cast<const double2*>(&sQ[u][2 * ty]);
+                    const double xp[4] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double d0 = xp[i] - qq.x, d1 = xp[i] - qq.y;
+                        D2[i][0] = fma(d0, d0, D2[i][0]);
+                        D2[i][1] = fma(d1, d1, D2[i][1]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    q[i][0][t] = (KER == 1) ? D2[i][0] : sqrt(D2[i][0]);
+                    q[i][1][t] = (KER == 1) ? D2[i][1] : sqrt(D2[i][1]);
+                }
+            }
+        }
+    }
+
+    const bool scaled = a.mult != 1.0;
+    const int gi0 = i0 + 4 * tx, gj0 = j0 + 2 * ty;
+    for (int b0 = 0; b0 < g.count; b0 += FBCH) {
+        const int nb = min(FBCH, g.count - b0);
+        __syncthreads();
+        for (int idx = tid; idx < nb * FNT; idx += ATHREADS) {
+            const int b = idx / FNT, t = idx % FNT;
+            double sc = 0.0;
+            if (t < nterms) {
+                const double* scale = a.elems ? a.elems[g.first + b0 + b].scale : a.scale + (long)(g.first + b0 + b) * a.nterms;
+                sc = scale[t];
+            }
+            sSc[b][t] = sc;
+            sSc2[b][t] = __dmul_rn(sc, sc);
+        }
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            double S[4][2], Pr[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { S[i][0] = 0.0; S[i][1] = 0.0; Pr[i][0] = 1.0; Pr[i][1] = 1.0; }
+#pragma unroll
+            for (int t = 0; t < FNT; ++t) {
+                if (t < nterms) {
+                    const double sc = sSc[b][t];
+                    if (KER == 1 && ((groupMask >> t) & 1u)) {
+                        const double sc2 = sSc2[b][t];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { S[i][0] = fma(q[i][0][t], sc2, S[i][0]); S[i][1] = fma(q[i][1][t], sc2, S[i][1]); }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const double av = __dmul_rn(q[i][j][t], sc);
+                                if (KER == 1) S[i][j] = fma(av, av, S[i][j]);
+                                else {
+                                    S[i][j] = __dadd_rn(S[i][j], av);
+                                    if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
+                                    else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
+                                }
+                            }
+                    }
+                }
+            }
+            double* M = a.M + (long)(g.first + b0 + b) * a.strideM;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int gj = gj0 + j;
+                if (gj >= a.nQ) continue;
+                double v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double r = (KER == 1) ? exp_nonpos(__dmul_rn(-0.5, S[i][j])) : __dmul_rn(Pr[i][j], exp_nonpos(-S[i][j]));
+                    if (a.rowOff + gi0 + i == a.colOff + gj) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
+                    else if (scaled) r = __dmul_rn(r, a.mult);
+                    v[i] = r;
+                }
+                double* colp = M + (long)(a.colOff + gj) * a.ld + a.rowOff;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int gi = gi0 + 2 * h;
+                    if (gi + 1 < a.nP && ((reinterpret_cast<uintptr_t>(colp + gi) & 15) == 0)) {
+                        *reinterpret_cast<double2*>(colp + gi) = make_double2(v[2 * h], v[2 * h + 1]);
+                    } else {
+                        if (gi < a.nP) colp[gi] = v[2 * h];
+                        if (gi + 1 < a.nP) colp[gi + 1] = v[2 * h + 1];
+                    }
+                }
             }
         }
     }
@@ -269,6 +453,23 @@ void launch_assemble(const AsmArgs& a, int batch, cudaStream_t st) {
     if (a.nP <= 0 || a.nQ <= 0 || batch <= 0) return;
     AsmK k{a, 0, a.nunits, nullptr};
     dispatch<MODE_STORE>(k, a.ker, dim3(ntiles_of(a), batch), st);
+}
+
+bool assemble_fusable(int nterms, int nunits) { return nterms >= 1 && nterms <= FNT && nunits <= FCC; }
+
+// symmetric training matrices of `ngroups` groups of batch elements; the elements of a group share structure and
+// coordinates (groups == nullptr: one group of `count` elements).  The caller has checked assemble_fusable().
+void launch_assemble_fused(const AsmArgs& a, const AsmGroup* groups, int ngroups, int count, cudaStream_t st) {
+    if (a.nP <= 0 || ngroups <= 0) return;
+    FusedK k{a, groups, count};
+    const int nT = (a.nP + FR - 1) / FR;
+    dim3 grid(nT * (nT + 1), ngroups);
+    FGP_COUNT_LAUNCH();
+    switch (a.ker) {
+        case 1: assemble_fused_kernel<1><<<grid, ATHREADS, 0, st>>>(k); break;
+        case 2: assemble_fused_kernel<2><<<grid, ATHREADS, 0, st>>>(k); break;
+        default: assemble_fused_kernel<3><<<grid, ATHREADS, 0, st>>>(k); break;
+    }
 }
 
 void launch_distmax(const double* X, int n, long ldX, const FgpUnit* units, int u0, int u1, double* out_max,

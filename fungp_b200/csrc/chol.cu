@@ -33,12 +33,29 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     const int colSegTile = (t.colHoleLo < t.ncols) ? t.colHoleHi / NBk : ncT;   // first tile of the second column segment
     FgpTimers* tm = ctx->profile ? &ctx->dev[devslot].timers : nullptr;
     const bool la_pre = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;
-    // Look-ahead path: the panel chain of one outer panel (outer x ~110 us) must hide under the trailing update of the
-    // previous one.  Measured (tools/single_probe*.py): n = 8192 best with 2 tiles per panel (10.1 ms; 4: 10.2), n = 16384
-    // with 8 (53.9 ms; 2: 58.8), n = 32768 with 16 (372 ms = 31.5 TFLOP/s; 2: 432)
-    const int outerSingle = ctx->outer_single > 0 ? ctx->outer_single : (ncT < 96 ? 2 : (ncT < 192 ? 8 : 16));
-    const int outer = std::max(1, la_pre ? outerSingle : ctx->outer);
+    // Look-ahead path: the panel chain of one outer panel must hide under the trailing update of the previous one.
+    // Round-1 measurements with one fixed width per factorisation (tools/single_probe*.py): n = 8192 best with 2 tiles per
+    // panel (10.1 ms; 4: 10.2), n = 16384 with 8 (53.9 ms; 2: 58.8), n = 32768 with 16 (372 ms = 31.5 TFLOP/s; 2: 432)
+    // Look-ahead schedule of a single factorisation, option "outer_single" = 0: the panel width follows the shape of the
+    // work.  A column tile costs the chain ~70 us (diagonal block, panel solve, narrow update) whatever the width, while
+    // the trailing update of r remaining tiles does ~0.06 r^2 us of work per 128 columns of K on 148 SMs: it hides the
+    // chain only while r > ~35.  So: start narrow (2 tiles: the device is busy after 150 us), widen to 8 (16 for very
+    // large matrices) while the update dominates -- wide K is where the DMMA kernel is efficient -- and return to 2-tile
+    // panels for the chain-bound tail.  A fixed width can still be forced with the option.
+    auto width_at = [&](int k) {
+        if (!la_pre) return std::max(1, ctx->outer);
+        if (ctx->outer_single > 0) return ctx->outer_single;
+        const int r = ncT - k;
+        if (ncT < 40) return 2;
+        if (k == 0) return 2;
+        if (k < 6) return 4;
+        if (r > 136) return 16;
+        if (r > 44) return 8;
+        if (r > 28) return 4;
+        return 2;
+    };
     (void)colHole;
+    const int pdlMode = (ctx->pdl && !ctx->graphs) ? (la_pre ? 2 : 1) : 0;      // not inside a stream capture
 
     auto col_nb = [&](int k) {
         const int k0 = k * NBk;
@@ -53,6 +70,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     base.colMin = 0; base.colLo = t.colHoleLo; base.colHoleHi = t.colHoleHi; base.ncols = t.ncols;
     base.batch = t.batch;
     base.maxTilesPerCta = la_pre ? 1 : 0;
+    base.pdl = pdlMode;
 
     cudaEvent_t evPanel = nullptr, evBulk = nullptr;
     const bool la = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;
@@ -132,6 +150,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     int k = 0;
     while (k < ncT) {
         // ---- outer panel [k, kend): never straddles the prefactored boundary or the column hole
+        const int outer = width_at(k);
         int kend = std::min(k + outer, ncT);
         if (k < t.cpre) kend = std::min(kend, t.cpre);
         if (k < colSegTile) kend = std::min(kend, colSegTile);
@@ -163,7 +182,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
             if (fresh) {
                 const int infoOff = (k0 >= t.colHoleHi && t.colHoleLo < t.ncols) ? (k0 - t.colHoleHi) : k0;
                 if (tm) tm->begin(sPanel);
-                launch_potf2(t.M, t.ld, t.strideM, t.batch, k0, nb, t.W, t.strideW, t.info, infoOff, sPanel);
+                launch_potf2(t.M, t.ld, t.strideM, t.batch, k0, nb, t.W, t.strideW, t.info, infoOff, sPanel, pdlMode);
                 if (tm) tm->end(sPanel, FgpTimers::PANEL, 0.0);
             }
             const RowSet S = rows_of(kk);
@@ -199,7 +218,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
                 if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
             } else {
                 // look-ahead: the next panel's columns on the panel stream (critical path), the rest on the bulk stream
-                int kend2 = std::min(kend + outer, ncT);
+                int kend2 = std::min(kend + width_at(kend), ncT);
                 if (kend < t.cpre) kend2 = std::min(kend2, t.cpre);
                 if (kend < colSegTile) kend2 = std::min(kend2, colSegTile);
                 cudaEventRecord(evPanel, sPanel);                           // panel solved

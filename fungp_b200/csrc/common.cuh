@@ -75,6 +75,11 @@ struct AsmArgs {
 };
 
 void launch_assemble(const AsmArgs& a, int batch, cudaStream_t st);
+// batch-fused assembly of symmetric training matrices: the elements of a group share structure and coordinates and
+// differ in their length-scales only (assemble.cu)
+struct AsmGroup { int first, count; };
+bool assemble_fusable(int nterms, int nunits);
+void launch_assemble_fused(const AsmArgs& a, const AsmGroup* groups, int ngroups, int count, cudaStream_t st);
 // max over pairs of the group distance of one L2_bygroup term / materialise one distance matrix
 void launch_distmax(const double* X, int n, long ldX, const FgpUnit* units, int u0, int u1, double* out_max,
                     cudaStream_t st);
@@ -104,7 +109,7 @@ struct FgpTimers;
 int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPanel, cudaStream_t sBulk, bool lookahead);
 
 void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, double* W, long strideW, int* info,
-                  int infoBase, cudaStream_t st);
+                  int infoBase, cudaStream_t st, int pdl = 0);
 
 struct GemmArgs {
     const double* A; long lda; long strideA;   // row operand: element (r, kk) = A[r + kk*lda], r = global row
@@ -124,6 +129,8 @@ struct GemmArgs {
     int bLowerTri;                             // 1: B(c, k) = 0 for k > c (panel solve with inv(L_kk)): skip the zero half
     int maxTilesPerCta;                        // 0 = automatic; 1 = one tile per CTA (look-ahead: the panel stream must find a free SM quickly)
     int dbg;                                   // experiment switches, honoured only when built with -DFGP_GEMM_DEBUG
+    int pdl;                                   // 1: programmatic dependent launch (the prologue overlaps the previous kernel's tail); 2: also
+                                               // release the dependents at once (single-factorisation chain: the next kernel waits resident)
 };
 void launch_gemm(const GemmArgs& g, cudaStream_t st);
 

@@ -103,6 +103,8 @@ struct fgp_ctx {
     int streams = 8;
     int fit_workers = 8;      // fgp_fit_batch, fit_mode 0: concurrent candidate fits (host threads) per GPU
     int fit_mode = 1;         // 1: lock-step -- one host thread per GPU advances all in-flight candidates together (fitlock.cu); 0: one thread per candidate
+    int pdl = 1;              // programmatic dependent launch along the factorisation's kernel chain
+    int fused_assembly = 1;   // batched likelihood calls assemble the matrices of one structure with the batch-fused kernel
     int fit_points = 0;       // lock-step: likelihood points per round and lane (0 = by memory, at most 512)
     int fit_lanes = 0;        // lock-step: rounds in flight per GPU (0 = 2 below n = 2048, else 1)
     int predict_reserve = 2048;   // rows kept free under the stored factor so that predict / simulate solve in place

@@ -73,7 +73,7 @@ struct Arena {
 };
 
 struct LockState {
-    Lane lane[2];
+    Lane lane[4];
     Arena arena;
     bool streamsReady = false;
 };
@@ -137,7 +137,7 @@ struct Driver {
         lmatBytes = sizeof(double) * (size_t)ldv * n;
         nlanes = wc->fit_lanes > 0 ? wc->fit_lanes : (n < 2048 ? 2 : 1);
         nst = n < 2048 ? 1 : (n < 4096 ? std::min(2, wc->streams) : wc->streams);
-        if (nlanes == 2) nst = std::min(nst, DevState::MAXSTREAMS / 2);
+        if (nlanes > 1) nst = std::min(nst, DevState::MAXSTREAMS / nlanes);
         if (!L->streamsReady) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -155,11 +155,20 @@ struct Driver {
         int maxNeed = npre, dmaxUnits = S.ds;
         for (int j = 0; j < S.df; ++j) dmaxUnits += S.k[j];
         maxUnits = std::max(1, dmaxUnits);
-        maxNeed = std::max(maxNeed, S.n_starts * (2 * std::min(S.dmax, dmaxUnits) + 1));
+        for (int c = 0; c < S.n_cand; ++c) {          // the largest finite-difference batch any structure of the call needs
+            const int* ant = S.ants + (size_t)c * S.antLen;
+            int dc = 0;
+            for (int i = 0; i < S.ds; ++i) dc += ant[i] == 1;
+            for (int j = 0; j < S.df; ++j) {
+                const int* a = ant + S.ds + 4 * j;
+                if (a[0] == 1) dc += a[1] == FGP_DIST_BYINDEX ? (a[2] > 0 ? a[2] : S.k[j]) : 1;
+            }
+            if (dc <= S.dmax) maxNeed = std::max(maxNeed, S.n_starts * (2 * dc + 1));
+        }
         size_t freeB = 0, totB = 0;
         cudaMemGetInfo(&freeB, &totB);
         size_t have = 0;
-        for (int l = 0; l < 2; ++l) have += L->lane[l].work.cap + L->lane[l].wbuf.cap + L->lane[l].lwork.cap + L->lane[l].lwbuf.cap;
+        for (int l = 0; l < 4; ++l) have += L->lane[l].work.cap + L->lane[l].wbuf.cap + L->lane[l].lwork.cap + L->lane[l].lwbuf.cap;
         const size_t budget = std::min<size_t>((size_t)((freeB + have) * 0.6), (size_t)64 << 30) / nlanes;
         const size_t perPoint = matBytes + wBytes;
         const size_t perLoocv = lmatBytes + wBytes;
@@ -181,6 +190,7 @@ struct Driver {
             }
             // staging of a full round up front: growing a device buffer later would synchronise the whole device
             const size_t blobMax = al16(sizeof(AsmElem) * (size_t)capPoints) + al16(sizeof(AsmElem) * (size_t)capLoocv) +
+                                   al16(sizeof(AsmGroup) * (size_t)capPoints) +
                                    al16(sizeof(FgpUnit) * (size_t)maxUnits * (size_t)(capPoints + capLoocv)) +
                                    sizeof(double) * (size_t)(capPoints + capLoocv) * std::max(1, S.dmax) + 64;
             const size_t resMax = (sizeof(double) * 2 + sizeof(int)) * (size_t)capPoints + (sizeof(double) * 2 * (size_t)n + sizeof(int)) * capLoocv + 64;
@@ -454,13 +464,24 @@ struct Driver {
 
     // gather the lane's requests into one blob, launch the round on the lane's streams
     int launch_round(Lane& ln) {
-        // ---- slots, grouped by correlation family (the assembly kernel is specialised on it)
+        // ---- slots, grouped by correlation family (the assembly kernel is specialised on it); inside a family first the
+        // candidates whose points can share one batch-fused assembly (a group = the consecutive points of one candidate:
+        // same coordinates, different length-scales), then the rest
         int B = 0, Lc = 0;
-        int kerEnd[4] = {0, 0, 0, 0}, lkerEnd[4] = {0, 0, 0, 0};
+        int kerEnd[4] = {0, 0, 0, 0}, lkerEnd[4] = {0, 0, 0, 0}, fusedEnd[4] = {0, 0, 0, 0}, groupEnd[4] = {0, 0, 0, 0};
         size_t nScale = 0, nUnits = 0;
+        std::vector<AsmGroup> groups;
+        const bool useFused = wc->fused_assembly != 0;
+        auto fused = [useFused](const Cand* c) { return useFused && c->nreq >= 2 && assemble_fusable(c->d, (int)c->units.size()); };
         for (int ker = 1; ker <= 3; ++ker) {
             for (Cand* c : ln.cands)
-                if (c->ker == ker && c->nreq > 0) { c->slot0 = B; B += c->nreq; nScale += (size_t)c->nreq * c->d; }
+                if (c->ker == ker && c->nreq > 0 && fused(c)) {
+                    c->slot0 = B; B += c->nreq; nScale += (size_t)c->nreq * c->d;
+                    groups.push_back({c->slot0, c->nreq});
+                }
+            fusedEnd[ker] = B; groupEnd[ker] = (int)groups.size();
+            for (Cand* c : ln.cands)
+                if (c->ker == ker && c->nreq > 0 && !fused(c)) { c->slot0 = B; B += c->nreq; nScale += (size_t)c->nreq * c->d; }
             kerEnd[ker] = B;
         }
         for (int ker = 1; ker <= 3; ++ker) {
@@ -472,8 +493,9 @@ struct Driver {
         ln.Btot = B; ln.Lcnt = Lc;
         if (B == 0 && Lc == 0) return 0;
         FGP_COUNT_WORK(0, B); FGP_COUNT_WORK(1, Lc);
-        // ---- blob: elements | loocv elements | unit tables | length-scale multipliers
-        const size_t offElem = 0, offLelem = al16(sizeof(AsmElem) * (size_t)B), offUnits = offLelem + al16(sizeof(AsmElem) * (size_t)Lc);
+        // ---- blob: elements | loocv elements | fused groups | unit tables | length-scale multipliers
+        const size_t offElem = 0, offLelem = al16(sizeof(AsmElem) * (size_t)B), offGroups = offLelem + al16(sizeof(AsmElem) * (size_t)Lc);
+        const size_t offUnits = offGroups + al16(sizeof(AsmGroup) * groups.size());
         const size_t offScale = offUnits + al16(sizeof(FgpUnit) * nUnits), blobBytes = offScale + sizeof(double) * nScale;
         if (ln.ensure_pinned(&ln.hBlob, &ln.hBlobCap, blobBytes) || ln.blob.ensure(std::max<size_t>(blobBytes, 1 << 16))) {
             fgp_set_err(wc, "fgp_fit_batch: out of memory (round blob)");
@@ -484,6 +506,8 @@ struct Driver {
         AsmElem* hLE = (AsmElem*)(ln.hBlob + offLelem);
         FgpUnit* hU = (FgpUnit*)(ln.hBlob + offUnits);
         double* hS = (double*)(ln.hBlob + offScale);
+        if (!groups.empty()) memcpy(ln.hBlob + offGroups, groups.data(), sizeof(AsmGroup) * groups.size());
+        const AsmGroup* dG = (const AsmGroup*)(dB + offGroups);
         const double* arenaX = (const double*)L->arena.buf.p;
         size_t uPos = 0, sPos = 0;
         for (Cand* c : ln.cands) {
@@ -520,7 +544,23 @@ struct Driver {
         cudaStream_t s0 = ln.st[0];
         LCK(cudaMemcpyAsync(dB, ln.hBlob, blobBytes, cudaMemcpyHostToDevice, s0));
         LCK(cudaMemsetAsync(dInfo, 0, resBytes - offInfo, s0));
-        // ---- likelihood points: groups of slots on the lane's streams (one group below n = 2048)
+        // ---- assembly of every point of the round on the lane's first stream: one batch-fused launch per correlation
+        // family over the candidates' groups, one plain launch for the rest
+        for (int ker = 1; ker <= 3 && B > 0; ++ker) {
+            AsmArgs a{};
+            a.XP = arenaX; a.nP = n; a.ldP = n; a.XQ = arenaX; a.nQ = n; a.ldQ = n;
+            a.ker = ker; a.sym = 1; a.mult = 1.0; a.diag_rel = S.nugget; a.diag_abs = 0.0;
+            a.ld = ld; a.strideM = (long)ld * n;
+            if (groupEnd[ker] > groupEnd[ker - 1]) {
+                a.M = (double*)ln.work.p; a.elems = dE;                  // groups carry absolute slot numbers
+                launch_assemble_fused(a, dG + groupEnd[ker - 1], groupEnd[ker] - groupEnd[ker - 1], 0, s0);
+            }
+            if (kerEnd[ker] > fusedEnd[ker]) {
+                a.M = (double*)ln.work.p + (size_t)fusedEnd[ker] * ld * n; a.elems = dE + fusedEnd[ker];
+                launch_assemble(a, kerEnd[ker] - fusedEnd[ker], s0);
+            }
+        }
+        // ---- factorisations: groups of slots on the lane's streams (one group below n = 2048)
         const int ns = B > 0 ? std::max(1, std::min(nst, B)) : 0;
         if (ns > 1) LCK(cudaEventRecord(ln.evFork, s0));
         const int per = ns ? cdiv(B, ns) : 0;
@@ -530,17 +570,6 @@ struct Driver {
             cudaStream_t st = ln.st[s];
             if (s > 0) LCK(cudaStreamWaitEvent(st, ln.evFork, 0));
             double* Mg = (double*)ln.work.p + (size_t)g0 * ld * n;
-            for (int ker = 1; ker <= 3; ++ker) {
-                const int a0 = std::max(g0, kerEnd[ker - 1]), a1 = std::min(g1, kerEnd[ker]);
-                if (a1 <= a0) continue;
-                AsmArgs a{};
-                a.XP = arenaX; a.nP = n; a.ldP = n; a.XQ = arenaX; a.nQ = n; a.ldQ = n;
-                a.units = nullptr; a.nunits = 0; a.scale = nullptr; a.nterms = 0; a.ker = ker; a.sym = 1;
-                a.mult = 1.0; a.diag_rel = S.nugget; a.diag_abs = 0.0;
-                a.M = (double*)ln.work.p + (size_t)a0 * ld * n; a.ld = ld; a.strideM = (long)ld * n;
-                a.elems = dE + a0;
-                launch_assemble(a, a1 - a0, st);
-            }
             launch_fill_yrow_elems(Mg, ld, (long)ld * n, g1 - g0, n, dE + g0, n, st);
             TrapDesc t{};
             t.M = Mg; t.ld = ld; t.strideM = (long)ld * n; t.batch = g1 - g0;
@@ -697,6 +726,7 @@ int fit_lockstep(fgp_ctx* ctx, Shared& S, const std::vector<int>& order) {
             cudaSetDevice(device);
             wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
             wc->fit_points = ctx->fit_points; wc->fit_lanes = ctx->fit_lanes; wc->predict_reserve = ctx->predict_reserve;
+            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl;
             wc->blockingSync = ctx->fit_blocking > 0 ? ctx->fit_blocking : 0;
             Driver drv(ctx, wc, S, order);
             rcs[dI] = drv.run();

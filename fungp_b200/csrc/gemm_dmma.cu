@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g, 
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    // programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream; its
+    // results are visible from here on.  Every kernel of the chain executes the wait (ordering stays transitive).
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (g.pdl == 2) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     int tIdx = blockIdx.x;
     if (tIdx >= ntiles) return;
     // ---- prologue of the first tile: STAGES-1 chunks in flight
@@ -410,5 +414,17 @@ void launch_gemm(const GemmArgs& g, cudaStream_t st) {
     if (g.dbg & 32) gx = ntiles;
     dim3 grid(gx, g.batch);
     FGP_COUNT_LAUNCH();
+    if (g.pdl) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM + 64; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        GemmArgs gg = g;
+        if (gg.pdl == 2 && (long)gx * g.batch > sms) gg.pdl = 1;     // early release only when the whole grid is resident at once
+        cudaLaunchKernelEx(&cfg, gemm_dmma_kernel, gg, ntiles);
+        return;
+    }
     gemm_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM + 64, st>>>(g, ntiles);     // + 2*STAGES mbarriers
 }

@@ -80,7 +80,7 @@ __device__ long long g_potf2_prof[32];
 #endif
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
-potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, long strideW, int* info, int infoOff) {
+potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, long strideW, int* info, int infoOff, int pdl) {
     extern __shared__ __align__(16) double sm[];
     double* T = sm;                       // 128 x 132
     double* XP = sm + NB * LDT;           // 32 x 132: XP[k*XLD + row] = staged panel X(row, k)
@@ -101,6 +101,9 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
     double* Mb = M + (long)blockIdx.x * strideM;
     double* Wb = W + (long)blockIdx.x * strideW + (long)(k0 / NB) * NB * NB;
 
+    // programmatic dependent launch: the barrier set-up above overlapped the previous kernel's tail
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (pdl == 2) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     PROF(0);
     // ---- load the lower triangle (identity padding for a ragged block, zeros above the diagonal)
     if (nb == NB) {
@@ -328,7 +331,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
 }  // namespace
 
 void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, double* W, long strideW, int* info,
-                  int infoOff, cudaStream_t st) {
+                  int infoOff, cudaStream_t st, int pdl) {
     static bool attr_set[FGP_MAXDEV] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -337,5 +340,15 @@ void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, d
         attr_set[dev] = true;
     }
     FGP_COUNT_LAUNCH();
-    potf2_inv_kernel<<<batch, POTF2_THREADS, POTF2_SMEM, st>>>(M, ld, strideM, k0, nb, W, strideW, info, infoOff);
+    if (pdl) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(batch); cfg.blockDim = dim3(POTF2_THREADS); cfg.dynamicSmemBytes = POTF2_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, potf2_inv_kernel, M, ld, strideM, k0, nb, W, strideW, info, infoOff, pdl);
+        return;
+    }
+    potf2_inv_kernel<<<batch, POTF2_THREADS, POTF2_SMEM, st>>>(M, ld, strideM, k0, nb, W, strideW, info, infoOff, 0);
 }

@@ -656,3 +656,31 @@ def test_near_duplicate_points_relative_distance(ctx):
     assert rel_far.max() <= 1e-10          # cond(J) ~ 1e6+ amplifies the rounding of c W on ordinary pairs: still 1e-10
     assert np.median(rel_cuda) <= 10.0 * max(np.median(rel_ref), 1e-9)
     assert np.all(np.isfinite(D)) and np.all(D >= 0.0) and np.array_equal(D, D.T)
+
+
+@pytest.mark.parametrize("ker", ["gauss", "matern5_2", "matern3_2"])
+def test_batch_fused_assembly_is_bit_identical(ctx, ker):
+    """The batch-fused assembly kernel (csrc/assemble.cu assemble_fused_kernel: coordinate differences once per tile, then
+    one pass per length-scale vector) against the per-matrix kernel: same operations in the same order, so the likelihood
+    of every batch element is the same to the last bit -- ragged n, index and group terms, 13- and 40-point batches."""
+    for seed, n, ds, f_lens, pdims, dis in ((61, 1000, 2, [30, 40], [5, 3], ["L2_bygroup", "L2_byindex"]),
+                                            (62, 333, 4, [20, 20], [5, 5], ["L2_bygroup", "L2_bygroup"]),
+                                            (63, 130, 1, [], [], [])):
+        case = make_case(seed, n, ds, f_lens, pdims, ["B-splines"] * len(f_lens), dis)
+        P = _problem(ctx, case)
+        ub = 2.0 * P.dist_max()
+        rng = np.random.default_rng(seed)
+        out = {}
+        try:
+            for B in (13, 40):
+                th = ub[:, None] * rng.uniform(0.1, 0.6, size=(P.d, B))
+                for fused in (0, 1):
+                    ctx.set_option("fused_assembly", fused)
+                    out[(B, fused)] = P.nll_batch(ker, 1e-8, th)
+        finally:
+            ctx.set_option("fused_assembly", 1)
+        for B in (13, 40):
+            a, b = out[(B, 0)], out[(B, 1)]
+            assert (a[2] == 0).all()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), (n, B)
+        P.close()

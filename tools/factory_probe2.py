@@ -1,5 +1,5 @@
 """Factory arm of bench.py under different driver options (GPU box): candidates/s, likelihood evaluations/s, TFLOP/s.
-usage: python tools/factory_probe2.py N_CAND  [mode:points:lanes ...]   e.g.  512 1:512:2 1:256:2 1:1024:1 0:0:0"""
+usage: python tools/factory_probe2.py N_CAND  [mode:points:lanes[:fused_assembly] ...]   e.g.  512 1:512:2 1:256:2 1:1024:1 0:0:0"""
 import json
 import os
 import sys
@@ -22,8 +22,11 @@ ants = bench.factory_candidates(ncand, F["list_seed"])
 u01 = bench.factory_draws(ants)
 ref = None
 for cfg in configs:
-    mode, pts, lanes = [int(v) for v in cfg.split(":")]
+    parts = [int(v) for v in cfg.split(":")]
+    mode, pts, lanes = parts[:3]
+    fusedA = parts[3] if len(parts) > 3 else 1
     ctx.set_option("fit_mode", mode); ctx.set_option("fit_points", pts); ctx.set_option("fit_lanes", lanes)
+    ctx.set_option("fused_assembly", fusedA)
     if mode == 0:
         ctx.set_option("lookahead", 0)
     ctx.fit_batch(sIn, fIn, y, ants[:32], u01[:32], nugget=F["nugget"])
