@@ -35,7 +35,18 @@ static fgp_problem* get_prob(SEXP p) {
 }
 static void check(int rc, fgp_ctx* ctx, const char* what) {
     if (rc > 0) Rf_error("the leading minor of order %d is not positive definite", rc);   /* base::chol's message */
-    if (rc < 0) Rf_error("funGp/%s failed (%d): %s", what, rc, ctx ? fgp_last_error(ctx) : "no CUDA device");
+    if (rc < 0) Rf_error("funGp/%s failed (%d): %s", what, rc, ctx ? fgp_last_error(ctx) : "no context");
+}
+/* the context a problem handle was created in (kept alive as the external pointer's protected value): the library's
+ * error text for a failed call on that problem */
+static fgp_ctx* prob_ctx(SEXP prob) {
+    SEXP c = R_ExternalPtrProtected(prob);
+    return (TYPEOF(c) == EXTPTRSXP) ? (fgp_ctx*)R_ExternalPtrAddr(c) : NULL;
+}
+
+/* is this external pointer still alive?  FALSE after save()/load() (nil address) or for anything that is not a pointer */
+SEXP fgpR_ptr_valid(SEXP p) {
+    return Rf_ScalarLogical(TYPEOF(p) == EXTPTRSXP && R_ExternalPtrAddr(p) != NULL);
 }
 
 /* .Call(C_fgpR_ctx_create, n_gpus)  -- options(funGp.gpus=) / FUNGP_GPUS, 0 = all visible */
@@ -86,7 +97,7 @@ SEXP fgpR_problem_create(SEXP ctx, SEXP sIn, SEXP coefs, SEXP J, SEXP dis, SEXP 
 SEXP fgpR_dist_max(SEXP prob) {
     fgp_problem* q = get_prob(prob);
     SEXP out = PROTECT(Rf_allocVector(REALSXP, fgp_problem_nls(q)));
-    check(fgp_dist_max(q, REAL(out)), NULL, "dist_max");
+    check(fgp_dist_max(q, REAL(out)), prob_ctx(prob), "dist_max");
     UNPROTECT(1);
     return out;
 }
@@ -96,7 +107,7 @@ SEXP fgpR_dist_matrix(SEXP prob, SEXP l) {
     fgp_problem* q = get_prob(prob);
     const int n = fgp_problem_n(q);
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
-    check(fgp_dist_materialize(q, Rf_asInteger(l) - 1, REAL(out)), NULL, "dist_materialize");
+    check(fgp_dist_materialize(q, Rf_asInteger(l) - 1, REAL(out)), prob_ctx(prob), "dist_materialize");
     UNPROTECT(1);
     return out;
 }
@@ -106,7 +117,7 @@ SEXP fgpR_assemble(SEXP prob, SEXP ker, SEXP nugget, SEXP theta) {
     fgp_problem* q = get_prob(prob);
     const int n = fgp_problem_n(q);
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, n));
-    check(fgp_assemble(q, Rf_asInteger(ker), Rf_asReal(nugget), REAL(theta), REAL(out)), NULL, "assemble");
+    check(fgp_assemble(q, Rf_asInteger(ker), Rf_asReal(nugget), REAL(theta), REAL(out)), prob_ctx(prob), "assemble");
     UNPROTECT(1);
     return out;
 }
@@ -122,7 +133,7 @@ SEXP fgpR_nll_batch(SEXP prob, SEXP ker, SEXP nugget, SEXP thetas, SEXP var_know
     SEXP info = PROTECT(Rf_allocVector(INTSXP, B));
     int rc = fgp_nll_batch(q, Rf_asInteger(ker), Rf_asReal(nugget), B, REAL(thetas), Rf_isNull(var_known) ? NULL : &vk, REAL(nll),
                            REAL(s2), INTEGER(info));
-    check(rc, NULL, "nll_batch");
+    check(rc, prob_ctx(prob), "nll_batch");
     SET_VECTOR_ELT(out, 0, nll); SET_VECTOR_ELT(out, 1, s2); SET_VECTOR_ELT(out, 2, info);
     UNPROTECT(4);
     return out;
@@ -134,7 +145,7 @@ SEXP fgpR_premats(SEXP prob, SEXP ker, SEXP nugget, SEXP sig2, SEXP theta) {
     const int n = fgp_problem_n(q);
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
     SEXP L = PROTECT(Rf_allocMatrix(REALSXP, n, n)), z = PROTECT(Rf_allocMatrix(REALSXP, n, 1));
-    check(fgp_premats(q, Rf_asInteger(ker), Rf_asReal(nugget), Rf_asReal(sig2), REAL(theta), REAL(L), REAL(z)), NULL, "premats");
+    check(fgp_premats(q, Rf_asInteger(ker), Rf_asReal(nugget), Rf_asReal(sig2), REAL(theta), REAL(L), REAL(z)), prob_ctx(prob), "premats");
     SET_VECTOR_ELT(out, 0, L); SET_VECTOR_ELT(out, 1, z);
     UNPROTECT(3);
     return out;
@@ -159,7 +170,7 @@ SEXP fgpR_predict(SEXP prob, SEXP m_, SEXP sNew, SEXP coefsNew, SEXP detail) {
     if (full) { Ktp = PROTECT(Rf_allocMatrix(REALSXP, n, m)); Kpp = PROTECT(Rf_allocMatrix(REALSXP, m, m)); }
     int rc = fgp_predict(q, m, Rf_isNull(sNew) ? NULL : REAL(sNew), cp, full, REAL(mean), REAL(sd), full ? REAL(Ktp) : NULL,
                          full ? REAL(Kpp) : NULL);
-    check(rc, NULL, "predict");
+    check(rc, prob_ctx(prob), "predict");
     SET_VECTOR_ELT(out, 0, mean); SET_VECTOR_ELT(out, 1, sd);
     if (full) { SET_VECTOR_ELT(out, 2, Ktp); SET_VECTOR_ELT(out, 3, Kpp); }
     UNPROTECT(full ? 5 : 3);
@@ -177,7 +188,7 @@ SEXP fgpR_simulate(SEXP prob, SEXP m_, SEXP sNew, SEXP coefsNew, SEXP Z, SEXP nu
     SEXP sd = PROTECT(Rf_allocVector(REALSXP, m));
     int rc = fgp_simulate(q, m, Rf_isNull(sNew) ? NULL : REAL(sNew), cp, nsim, REAL(Z), Rf_asReal(nugget_sm), REAL(sims), REAL(mean),
                           REAL(sd));
-    check(rc, NULL, "simulate");
+    check(rc, prob_ctx(prob), "simulate");
     SET_VECTOR_ELT(out, 0, sims); SET_VECTOR_ELT(out, 1, mean); SET_VECTOR_ELT(out, 2, sd);
     UNPROTECT(4);
     return out;
@@ -189,7 +200,7 @@ SEXP fgpR_loocv(SEXP prob) {
     const int n = fgp_problem_n(q);
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
     SEXP yp = PROTECT(Rf_allocMatrix(REALSXP, n, 1)), q2 = PROTECT(Rf_allocVector(REALSXP, 1));
-    check(fgp_loocv(q, REAL(yp), REAL(q2)), NULL, "loocv");
+    check(fgp_loocv(q, REAL(yp), REAL(q2)), prob_ctx(prob), "loocv");
     SET_VECTOR_ELT(out, 0, yp); SET_VECTOR_ELT(out, 1, q2);
     UNPROTECT(3);
     return out;
@@ -197,7 +208,7 @@ SEXP fgpR_loocv(SEXP prob) {
 
 /* output substitution of update() (R/6_updating.R:154-160) */
 SEXP fgpR_set_y(SEXP prob, SEXP y) {
-    check(fgp_problem_set_y(get_prob(prob), REAL(y)), NULL, "set_y");
+    check(fgp_problem_set_y(get_prob(prob), REAL(y)), prob_ctx(prob), "set_y");
     return R_NilValue;
 }
 
@@ -212,11 +223,15 @@ SEXP fgpR_fit_batch(SEXP ctx, SEXP sIn, SEXP fIn, SEXP sOut, SEXP antsT, SEXP nu
     const int n_cand = Rf_ncols(antsT), dmax = Rf_asInteger(dmax_);
     const int n_rep = Rf_isNull(ind_vl) ? 0 : Rf_ncols(ind_vl), n_vl = Rf_isNull(ind_vl) ? 0 : Rf_nrows(ind_vl);
     const int items = n_cand * (n_rep > 0 ? n_rep : 1);
-    const double* fp[64]; int k[64]; long long off[4096];
+    const double* fp[64]; int k[64];
     if (df > 64) Rf_error("funGp: more than 64 functional inputs");
-    if (items > 4096 || Rf_length(u01_off) != items) Rf_error("funGp: u01_off must have one entry per work item (<= 4096)");
+    if (Rf_length(u01_off) != items) Rf_error("funGp: u01_off must have one entry per work item");
+    long long* off = (long long*)R_alloc((size_t)(items > 0 ? items : 1), sizeof(long long));
     for (int j = 0; j < df; ++j) { fp[j] = REAL(VECTOR_ELT(fIn, j)); k[j] = Rf_ncols(VECTOR_ELT(fIn, j)); }
     for (int i = 0; i < items; ++i) off[i] = (long long)REAL(u01_off)[i];
+    /* the colony's ant matrix and ind.vl are double matrices in R unless coerced: never read them through INTEGER() as is */
+    antsT = PROTECT(Rf_coerceVector(antsT, INTSXP));
+    ind_vl = PROTECT(Rf_isNull(ind_vl) ? ind_vl : Rf_coerceVector(ind_vl, INTSXP));
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 5));
     SEXP fit = PROTECT(Rf_allocVector(REALSXP, items)), nll = PROTECT(Rf_allocVector(REALSXP, items));
     SEXP s2 = PROTECT(Rf_allocVector(REALSXP, items)), th = PROTECT(Rf_allocMatrix(REALSXP, dmax, items));
@@ -233,6 +248,44 @@ SEXP fgpR_fit_batch(SEXP ctx, SEXP sIn, SEXP fIn, SEXP sOut, SEXP antsT, SEXP nu
     check(rc, get_ctx(ctx), "fit_batch");
     SET_VECTOR_ELT(out, 0, fit); SET_VECTOR_ELT(out, 1, nll); SET_VECTOR_ELT(out, 2, s2); SET_VECTOR_ELT(out, 3, th);
     SET_VECTOR_ELT(out, 4, info);
-    UNPROTECT(6);
+    UNPROTECT(8);
+    return out;
+}
+
+/* (de)serialisation: hand the stored preMats of a loaded model back to a fresh problem handle -- no factorisation
+ * .Call(fgpR_restore, prob, ker, nugget, sig2, theta, L, LInvY) */
+SEXP fgpR_restore(SEXP prob, SEXP ker, SEXP nugget, SEXP sig2, SEXP theta, SEXP L, SEXP z) {
+    check(fgp_problem_restore(get_prob(prob), Rf_asInteger(ker), Rf_asReal(nugget), Rf_asReal(sig2), REAL(theta), REAL(L), REAL(z)),
+          prob_ctx(prob), "problem_restore");
+    return R_NilValue;
+}
+
+/* update() fast paths (R/6_updating.R): -> list(L, LInvY) of the updated model */
+SEXP fgpR_update_var(SEXP prob, SEXP sig2_new) {
+    fgp_problem* q = get_prob(prob);
+    const int n = fgp_problem_n(q);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP L = PROTECT(Rf_allocMatrix(REALSXP, n, n)), z = PROTECT(Rf_allocMatrix(REALSXP, n, 1));
+    check(fgp_update_var(q, Rf_asReal(sig2_new), REAL(L), REAL(z)), prob_ctx(prob), "update_var");
+    SET_VECTOR_ELT(out, 0, L); SET_VECTOR_ELT(out, 1, z);
+    UNPROTECT(3);
+    return out;
+}
+SEXP fgpR_update_y(SEXP prob, SEXP y) {
+    fgp_problem* q = get_prob(prob);
+    SEXP z = PROTECT(Rf_allocMatrix(REALSXP, fgp_problem_n(q), 1));
+    check(fgp_update_y(q, REAL(y), REAL(z)), prob_ctx(prob), "update_y");
+    UNPROTECT(1);
+    return z;
+}
+SEXP fgpR_premats_reuse(SEXP prob_new, SEXP prob_old) {
+    fgp_problem* q = get_prob(prob_new);
+    const int n = fgp_problem_n(q);
+    int reused = 0;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP L = PROTECT(Rf_allocMatrix(REALSXP, n, n)), z = PROTECT(Rf_allocMatrix(REALSXP, n, 1));
+    check(fgp_premats_reuse(q, get_prob(prob_old), REAL(L), REAL(z), &reused), prob_ctx(prob_new), "premats_reuse");
+    SET_VECTOR_ELT(out, 0, L); SET_VECTOR_ELT(out, 1, z); SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(reused));
+    UNPROTECT(3);
     return out;
 }

@@ -8,6 +8,7 @@ typedef int Rboolean;
 #define INTSXP 13
 #define REALSXP 14
 #define VECSXP 19
+#define EXTPTRSXP 22
 extern SEXP R_NilValue;
 SEXP Rf_allocVector(unsigned int, long);
 SEXP Rf_allocMatrix(unsigned int, int, int);
@@ -30,6 +31,12 @@ void Rf_error(const char*, ...) __attribute__((noreturn));
 SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void* R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);
+SEXP R_ExternalPtrProtected(SEXP);
+int TYPEOF(SEXP);
+SEXP Rf_coerceVector(SEXP, unsigned int);
+SEXP Rf_ScalarLogical(int);
+SEXP Rf_ScalarInteger(int);
+char* R_alloc(unsigned long, int);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 #endif
