@@ -153,9 +153,10 @@ def run_factory(ctx, rank, world, n_cand, barrier):
                 first=(int(idx[0]), float(res["fitness"][0]), float(res["nll"][0])), data=(sIn, fIn, y, ants, u01))
 
 
-def factory_cpu_baseline(data, budget_s=25.0):
+def factory_cpu_baseline(data, budget_s=5.0):
     """The oracle (numpy/scipy restatement of fgpm() + Q2loocv, oracle/) on candidates of the same fixed list, with the same
-    presample draws, on the host cores: a bounded sample (whole candidates until the time budget is spent)."""
+    presample draws, on the host cores: a bounded sample (whole candidates until the time budget is spent -- one oracle
+    candidate at n = 1024 takes tens of seconds, so in practice the first candidate of the list)."""
     from oracle import fungp_ref as ref
     from fungp_b200 import factory as F
     sIn, fIn, y, ants, u01 = data
@@ -216,6 +217,12 @@ def run_ours(args):
     ctx.set_option("fit_blocking", args.fit_blocking)
     ctx.set_option("graphs", args.graphs)
     ctx.set_option("fit_mode", args.fit_mode)
+    ctx.set_option("pdl", args.pdl)
+    ctx.set_option("fused_assembly", args.fused)
+    if args.fit_lanes > 0:
+        ctx.set_option("fit_lanes", args.fit_lanes)
+    if args.fit_points > 0:
+        ctx.set_option("fit_points", args.fit_points)
     if args.fit_workers > 0:
         ctx.set_option("fit_workers", args.fit_workers)
     sIn, fIn, y = build_inputs()
@@ -555,6 +562,10 @@ def main():
     ap.add_argument("--factory-cands", type=int, default=FACTORY["n_cand"],
                     help="length of the fixed candidate list for the factory metric, sharded over the GPUs (0 = skip)")
     ap.add_argument("--fit-mode", type=int, default=1, help="fgp_fit_batch: 1 lock-step driver (one host thread per GPU), 0 one thread per candidate")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch along the factorisation chain (0/1)")
+    ap.add_argument("--fused", type=int, default=1, help="batch-fused assembly kernel (0/1)")
+    ap.add_argument("--fit-lanes", type=int, default=0, help="lock-step rounds in flight per GPU (0 = library default)")
+    ap.add_argument("--fit-points", type=int, default=0, help="lock-step likelihood points per round and lane (0 = library default)")
     ap.add_argument("--inproc-cands", type=int, default=256, help="N > 1: candidates rank 0 also scores through ONE context over all N GPUs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -558,7 +558,7 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
             if (prof) d.timers.begin(st);
             // the points of a batch share every coordinate difference: one batch-fused launch (bit-identical entries)
-            if (gb >= 2 && ctx->fused_assembly && assemble_fusable(nt, (int)P->units.size())) launch_assemble_fused(a, nullptr, 1, gb, st);
+            if (gb >= 4 && ctx->fused_assembly && assemble_fusable(nt, (int)P->units.size())) launch_assemble_fused(a, nullptr, 1, gb, st);
             else launch_assemble(a, gb, st);
             if (prof) d.timers.end(st, FgpTimers::ASSEMBLY, 0.0);
             launch_fill_yrow(Mg, ld, (long)ld * n, gb, n, pd.y, n, st);

@@ -258,9 +258,11 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
 // instructions per term + the 18 of the exp instead of 2-3 per coordinate + 18: the kernel moves from the FP64-issue
 // ceiling towards the HBM write roofline.  The arithmetic per entry is instruction for instruction that of
 // assemble_kernel (same operations in the same order), so both kernels produce bit-identical matrices.
-// Tile 64 rows x 32 columns, 256 threads, 4 x 2 entries per thread (the base quantities of 8 entries x up to 8 terms
-// live in registers); structures with more than 8 length-scales or 48 units use assemble_kernel.
+// Tile 64 rows x 32 columns, 512 threads, 4 x 1 entries per thread (the base quantities of 4 entries x up to 8 terms
+// live in registers, 16 warps hide the staging latency); structures with more than 8 length-scales or 48 units, and
+// batches of fewer than 4 points (too little to amortise the per-tile set-up), use assemble_kernel.
 constexpr int FR = 64, FC = 32;          // fused tile
+constexpr int FTHREADS = 512;            // 16 warps: 4 rows x 1 column per thread
 constexpr int FCC = 48;                  // units (coordinate columns) a fused tile can stage
 constexpr int FNT = 8;                   // length-scale terms
 constexpr int FBCH = 32;                 // batch elements whose multipliers are staged at a time
@@ -272,14 +274,14 @@ struct FusedK {
 };
 
 template <int KER>
-__global__ void __launch_bounds__(ATHREADS, 1) assemble_fused_kernel(FusedK k) {
+__global__ void __launch_bounds__(FTHREADS, 1) assemble_fused_kernel(FusedK k) {
     __shared__ __align__(16) double sP[FCC][FR];
     __shared__ __align__(16) double sQ[FCC][FC];
     __shared__ double sSc[FBCH][FNT], sSc2[FBCH][FNT];
     __shared__ int sCol[FCC], sFlag[FCC], sTermFirst[FNT + 1], sNterms;
     const AsmArgs& a = k.a;
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;             // rows 4tx..4tx+3, columns 2ty, 2ty+1
+    const int tx = tid & 15, ty = tid >> 4;             // rows 4tx..4tx+3, column ty
     // tile (I over 64-row blocks, J over 32-column blocks) with J <= 2I + 1: t = I (I + 1) + J
     int I = (int)((sqrtf(4.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
     while ((I + 1) * (I + 2) <= (int)blockIdx.x) ++I;
@@ -306,11 +308,11 @@ __global__ void __launch_bounds__(ATHREADS, 1) assemble_fused_kernel(FusedK k) {
             if (sFlag[u] & 2) sTermFirst[++t] = u + 1;
         sNterms = t;
     }
-    for (int idx = tid; idx < nunits * FR; idx += ATHREADS) {
+    for (int idx = tid; idx < nunits * FR; idx += FTHREADS) {
         const int c = idx / FR, pnt = idx % FR;
         sP[c][pnt] = (i0 + pnt < a.nP) ? X[(long)sCol[c] * a.ldP + i0 + pnt] : 0.0;
     }
-    for (int idx = tid; idx < nunits * FC; idx += ATHREADS) {
+    for (int idx = tid; idx < nunits * FC; idx += FTHREADS) {
         const int c = idx / FC, pnt = idx % FC;
         sQ[c][pnt] = (j0 + pnt < a.nQ) ? X[(long)sCol[c] * a.ldQ + j0 + pnt] : 0.0;
     }
@@ -318,53 +320,41 @@ __global__ void __launch_bounds__(ATHREADS, 1) assemble_fused_kernel(FusedK k) {
     const int nterms = sNterms;
 
     // ---- base quantity of every term: |x_i - x_j|, or the summed squares (gauss) / their root (Matern) of a group
-    double q[4][2][FNT];
+    double q[4][FNT];
     unsigned groupMask = 0;
 #pragma unroll
     for (int t = 0; t < FNT; ++t) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { q[i][0][t] = 0.0; q[i][1][t] = 0.0; }
+        for (int i = 0; i < 4; ++i) q[i][t] = 0.0;
         if (t < nterms) {
             const int u0 = sTermFirst[t], u1 = sTermFirst[t + 1];
             if (!(sFlag[u0] & 1)) {
                 const double2 p01 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx]);
                 const double2 p23 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx + 2]);
-                const double2 qq = *reinterpret_cast<const double2*>(&sQ[u0][2 * ty]);
-                const double xp[4] = {p01.x, p01.y, p23.x, p23.y};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { q[i][0][t] = fabs(xp[i] - qq.x); q[i][1][t] = fabs(xp[i] - qq.y); }
+                const double xq = sQ[u0][ty];
+                q[0][t] = fabs(p01.x - xq); q[1][t] = fabs(p01.y - xq); q[2][t] = fabs(p23.x - xq); q[3][t] = fabs(p23.y - xq);
             } else {
                 groupMask |= 1u << t;
-                double D2[4][2];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { D2[i][0] = 0.0; D2[i][1] = 0.0; }
+                double D2[4] = {0.0, 0.0, 0.0, 0.0};
                 for (int u = u0; u < u1; ++u) {
                     const double2 p01 = *reinterpret_cast<const double2*>(&sP[u][4 * tx]);
                     const double2 p23 = *reinterpret_cast<const double2*>(&sP[u][4 * tx + 2]);
-                    const double2 qq = *reinterpret_cast<const double2*>(&sQ[u][2 * ty]);
-                    const double xp[4] = {p01.x, p01.y, p23.x, p23.y};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double d0 = xp[i] - qq.x, d1 = xp[i] - qq.y;
-                        D2[i][0] = fma(d0, d0, D2[i][0]);
-                        D2[i][1] = fma(d1, d1, D2[i][1]);
-                    }
+                    const double xq = sQ[u][ty];
+                    const double d0 = p01.x - xq, d1 = p01.y - xq, d2 = p23.x - xq, d3 = p23.y - xq;
+                    D2[0] = fma(d0, d0, D2[0]); D2[1] = fma(d1, d1, D2[1]); D2[2] = fma(d2, d2, D2[2]); D2[3] = fma(d3, d3, D2[3]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    q[i][0][t] = (KER == 1) ? D2[i][0] : sqrt(D2[i][0]);
-                    q[i][1][t] = (KER == 1) ? D2[i][1] : sqrt(D2[i][1]);
-                }
+                for (int i = 0; i < 4; ++i) q[i][t] = (KER == 1) ? D2[i] : sqrt(D2[i]);
             }
         }
     }
 
     const bool scaled = a.mult != 1.0;
-    const int gi0 = i0 + 4 * tx, gj0 = j0 + 2 * ty;
+    const int gi0 = i0 + 4 * tx, gj = j0 + ty;
     for (int b0 = 0; b0 < g.count; b0 += FBCH) {
         const int nb = min(FBCH, g.count - b0);
         __syncthreads();
-        for (int idx = tid; idx < nb * FNT; idx += ATHREADS) {
+        for (int idx = tid; idx < nb * FNT; idx += FTHREADS) {
             const int b = idx / FNT, t = idx % FNT;
             double sc = 0.0;
             if (t < nterms) {
@@ -375,10 +365,9 @@ __global__ void __launch_bounds__(ATHREADS, 1) assemble_fused_kernel(FusedK k) {
             sSc2[b][t] = __dmul_rn(sc, sc);
         }
         __syncthreads();
+        if (gj >= a.nQ) continue;
         for (int b = 0; b < nb; ++b) {
-            double S[4][2], Pr[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { S[i][0] = 0.0; S[i][1] = 0.0; Pr[i][0] = 1.0; Pr[i][1] = 1.0; }
+            double S[4] = {0.0, 0.0, 0.0, 0.0}, Pr[4] = {1.0, 1.0, 1.0, 1.0};
 #pragma unroll
             for (int t = 0; t < FNT; ++t) {
                 if (t < nterms) {
@@ -386,46 +375,38 @@ __global__ void __launch_bounds__(ATHREADS, 1) assemble_fused_kernel(FusedK k) {
                     if (KER == 1 && ((groupMask >> t) & 1u)) {
                         const double sc2 = sSc2[b][t];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { S[i][0] = fma(q[i][0][t], sc2, S[i][0]); S[i][1] = fma(q[i][1][t], sc2, S[i][1]); }
+                        for (int i = 0; i < 4; ++i) S[i] = fma(q[i][t], sc2, S[i]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const double av = __dmul_rn(q[i][j][t], sc);
-                                if (KER == 1) S[i][j] = fma(av, av, S[i][j]);
-                                else {
-                                    S[i][j] = __dadd_rn(S[i][j], av);
-                                    if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
-                                    else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
-                                }
+                        for (int i = 0; i < 4; ++i) {
+                            const double av = __dmul_rn(q[i][t], sc);
+                            if (KER == 1) S[i] = fma(av, av, S[i]);
+                            else {
+                                S[i] = __dadd_rn(S[i], av);
+                                if (KER == 2) Pr[i] = __dmul_rn(Pr[i], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
+                                else Pr[i] = __dmul_rn(Pr[i], __dadd_rn(1.0, av));
                             }
+                        }
                     }
                 }
             }
-            double* M = a.M + (long)(g.first + b0 + b) * a.strideM;
+            double v[4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int gj = gj0 + j;
-                if (gj >= a.nQ) continue;
-                double v[4];
+            for (int i = 0; i < 4; ++i) {
+                double r = (KER == 1) ? exp_nonpos(__dmul_rn(-0.5, S[i])) : __dmul_rn(Pr[i], exp_nonpos(-S[i]));
+                if (a.rowOff + gi0 + i == a.colOff + gj) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
+                else if (scaled) r = __dmul_rn(r, a.mult);
+                v[i] = r;
+            }
+            double* colp = a.M + (long)(g.first + b0 + b) * a.strideM + (long)(a.colOff + gj) * a.ld + a.rowOff;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    double r = (KER == 1) ? exp_nonpos(__dmul_rn(-0.5, S[i][j])) : __dmul_rn(Pr[i][j], exp_nonpos(-S[i][j]));
-                    if (a.rowOff + gi0 + i == a.colOff + gj) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
-                    else if (scaled) r = __dmul_rn(r, a.mult);
-                    v[i] = r;
-                }
-                double* colp = M + (long)(a.colOff + gj) * a.ld + a.rowOff;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int gi = gi0 + 2 * h;
-                    if (gi + 1 < a.nP && ((reinterpret_cast<uintptr_t>(colp + gi) & 15) == 0)) {
-                        *reinterpret_cast<double2*>(colp + gi) = make_double2(v[2 * h], v[2 * h + 1]);
-                    } else {
-                        if (gi < a.nP) colp[gi] = v[2 * h];
-                        if (gi + 1 < a.nP) colp[gi + 1] = v[2 * h + 1];
-                    }
+            for (int h = 0; h < 2; ++h) {
+                const int gi = gi0 + 2 * h;
+                if (gi + 1 < a.nP && ((reinterpret_cast<uintptr_t>(colp + gi) & 15) == 0)) {
+                    *reinterpret_cast<double2*>(colp + gi) = make_double2(v[2 * h], v[2 * h + 1]);
+                } else {
+                    if (gi < a.nP) colp[gi] = v[2 * h];
+                    if (gi + 1 < a.nP) colp[gi + 1] = v[2 * h + 1];
                 }
             }
         }
@@ -466,9 +447,9 @@ void launch_assemble_fused(const AsmArgs& a, const AsmGroup* groups, int ngroups
     dim3 grid(nT * (nT + 1), ngroups);
     FGP_COUNT_LAUNCH();
     switch (a.ker) {
-        case 1: assemble_fused_kernel<1><<<grid, ATHREADS, 0, st>>>(k); break;
-        case 2: assemble_fused_kernel<2><<<grid, ATHREADS, 0, st>>>(k); break;
-        default: assemble_fused_kernel<3><<<grid, ATHREADS, 0, st>>>(k); break;
+        case 1: assemble_fused_kernel<1><<<grid, FTHREADS, 0, st>>>(k); break;
+        case 2: assemble_fused_kernel<2><<<grid, FTHREADS, 0, st>>>(k); break;
+        default: assemble_fused_kernel<3><<<grid, FTHREADS, 0, st>>>(k); break;
     }
 }
 

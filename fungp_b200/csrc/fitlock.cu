@@ -472,7 +472,7 @@ struct Driver {
         size_t nScale = 0, nUnits = 0;
         std::vector<AsmGroup> groups;
         const bool useFused = wc->fused_assembly != 0;
-        auto fused = [useFused](const Cand* c) { return useFused && c->nreq >= 2 && assemble_fusable(c->d, (int)c->units.size()); };
+        auto fused = [useFused](const Cand* c) { return useFused && c->nreq >= 4 && assemble_fusable(c->d, (int)c->units.size()); };
         for (int ker = 1; ker <= 3; ++ker) {
             for (Cand* c : ln.cands)
                 if (c->ker == ker && c->nreq > 0 && fused(c)) {

@@ -124,7 +124,11 @@ def test_update_fast_paths_vs_oracle_refit(ctx, n):
         assert Lg.shape == Lo.shape, what
         assert np.max(np.abs(Lg - Lo)) <= 1e-9 * np.max(np.abs(Lo)), what
         assert np.all(np.triu(Lg, 1) == 0.0), what
-        assert np.max(np.abs(gm.preMats["LInvY"] - o.LInvY)) <= 1e-8 * np.max(np.abs(o.LInvY)), what
+        # L^-1 y at a fitted optimum (cond ~1e9 at n = 2048) is only determined to cond * eps: forward tolerance 1e-6, and
+        # the backward error -- L z reproduces y -- at 1e-12 of |L| |z|
+        zg = gm.preMats["LInvY"].ravel()
+        assert np.max(np.abs(zg - o.LInvY.ravel())) <= 1e-6 * np.max(np.abs(o.LInvY)), what
+        assert np.max(np.abs(Lg @ zg - oy)) <= 1e-12 * np.max(np.abs(Lg) @ np.abs(zg)), what
         assert gm.reused_points >= min_reuse, (what, gm.reused_points)
         pg = M.predict(gm, sIn_pr=sIn[te][:9], fIn_pr=[f[te][:9] for f in fIn])
         po = ref.predict(o, sNew=sIn[te][:9], fNew=[f[te][:9] for f in fIn])
