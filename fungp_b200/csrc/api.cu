@@ -57,6 +57,7 @@ static inline long pick_ld(long rows) { return fgp_pick_ld(rows); }
 
 std::atomic<long long> g_fgp_launches{0};
 std::atomic<long long> g_fgp_work[4];
+extern int g_plain_tma;
 
 extern "C" const char* fgp_version(void) { return "fungp_b200 0.1 (sm_100a, FP64 DMMA)"; }
 
@@ -138,6 +139,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "fit_mode")) ctx->fit_mode = value != 0 ? 1 : 0;
     else if (!strcmp(name, "pdl")) ctx->pdl = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value != 0 ? 1 : 0; g_plain_tma = ctx->gemm_tma; }
     else if (!strcmp(name, "fused_assembly")) ctx->fused_assembly = value != 0 ? 1 : 0;
     else if (!strcmp(name, "fit_points")) ctx->fit_points = std::max(0, std::min((int)value, 4096));
     else if (!strcmp(name, "fit_lanes")) ctx->fit_lanes = std::max(0, std::min((int)value, 4));

@@ -258,11 +258,12 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
 // instructions per term + the 18 of the exp instead of 2-3 per coordinate + 18: the kernel moves from the FP64-issue
 // ceiling towards the HBM write roofline.  The arithmetic per entry is instruction for instruction that of
 // assemble_kernel (same operations in the same order), so both kernels produce bit-identical matrices.
-// Tile 64 rows x 32 columns, 512 threads, 4 x 1 entries per thread (the base quantities of 4 entries x up to 8 terms
-// live in registers, 16 warps hide the staging latency); structures with more than 8 length-scales or 48 units, and
-// batches of fewer than 4 points (too little to amortise the per-tile set-up), use assemble_kernel.
-constexpr int FR = 64, FC = 32;          // fused tile
-constexpr int FTHREADS = 512;            // 16 warps: 4 rows x 1 column per thread
+// Tile 64 rows x 16 columns, 256 threads, 4 x 1 entries per thread (the base quantities of 4 entries x up to 8 terms
+// live in registers; 124 registers, so two CTAs share an SM and hide each other's staging); structures with more than 8
+// length-scales or 48 units, and batches of fewer than 4 points (too little to amortise the per-tile set-up), use
+// assemble_kernel.
+constexpr int FR = 64, FC = 16;          // fused tile
+constexpr int FTHREADS = 256;            // 8 warps: 4 rows x 1 column per thread; two CTAs per SM hide each other's set-up
 constexpr int FCC = 48;                  // units (coordinate columns) a fused tile can stage
 constexpr int FNT = 8;                   // length-scale terms
 constexpr int FBCH = 32;                 // batch elements whose multipliers are staged at a time
@@ -274,7 +275,7 @@ struct FusedK {
 };
 
 template <int KER>
-__global__ void __launch_bounds__(FTHREADS, 1) assemble_fused_kernel(FusedK k) {
+__global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
     __shared__ __align__(16) double sP[FCC][FR];
     __shared__ __align__(16) double sQ[FCC][FC];
     __shared__ double sSc[FBCH][FNT], sSc2[FBCH][FNT];
@@ -282,11 +283,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) assemble_fused_kernel(FusedK k) {
     const AsmArgs& a = k.a;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;             // rows 4tx..4tx+3, column ty
-    // tile (I over 64-row blocks, J over 32-column blocks) with J <= 2I + 1: t = I (I + 1) + J
-    int I = (int)((sqrtf(4.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
-    while ((I + 1) * (I + 2) <= (int)blockIdx.x) ++I;
-    while (I * (I + 1) > (int)blockIdx.x) --I;
-    const int J = blockIdx.x - I * (I + 1);
+    // tile (I over 64-row blocks, J over 16-column blocks) with J < R (I + 1), R = FR / FC:  t = R I (I + 1) / 2 + J
+    constexpr int R = FR / FC;
+    int I = (int)((sqrtf(8.0f * (float)blockIdx.x / (float)R + 1.0f) - 1.0f) * 0.5f);
+    while (R * (I + 1) * (I + 2) / 2 <= (int)blockIdx.x) ++I;
+    while (R * I * (I + 1) / 2 > (int)blockIdx.x) --I;
+    const int J = blockIdx.x - R * I * (I + 1) / 2;
     const int i0 = I * FR, j0 = J * FC;
     AsmGroup g;
     if (k.groups) g = k.groups[blockIdx.y];
@@ -444,7 +446,7 @@ void launch_assemble_fused(const AsmArgs& a, const AsmGroup* groups, int ngroups
     if (a.nP <= 0 || ngroups <= 0) return;
     FusedK k{a, groups, count};
     const int nT = (a.nP + FR - 1) / FR;
-    dim3 grid(nT * (nT + 1), ngroups);
+    dim3 grid((FR / FC) * nT * (nT + 1) / 2, ngroups);
     FGP_COUNT_LAUNCH();
     switch (a.ker) {
         case 1: assemble_fused_kernel<1><<<grid, FTHREADS, 0, st>>>(k); break;

@@ -71,6 +71,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     base.batch = t.batch;
     base.maxTilesPerCta = la_pre ? 1 : 0;
     base.pdl = pdlMode;
+    base.tma = ctx->gemm_tma;
 
     cudaEvent_t evPanel = nullptr, evBulk = nullptr;
     const bool la = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;
@@ -506,13 +507,15 @@ void launch_trtri_blocks(const double* M, long ld, int n, double* W, cudaStream_
     trtri_blocks_kernel<<<cdiv(n, FGP_TILE), FGP_TILE, smem, st>>>(M, ld, n, W);
 }
 
+int g_plain_tma = 1;      // operand path of launch_gemm_plain (set with the context option "gemm_tma")
+
 // C (rows x cols of 128-tiles, lower triangle only when `tri`) -= A B' over K columns: plain operands without holes.
 // rows / cols are the valid extents (ragged last tiles are masked).
 void launch_gemm_plain(const double* A, long lda, const double* B, long ldb, double* C, long ldc, int rows, int cols, int K,
                        bool tri, cudaStream_t st) {
     GemmArgs g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
-    g.K = K; g.accumulate = 1; g.batch = 1;
+    g.K = K; g.accumulate = 1; g.batch = 1; g.tma = g_plain_tma;
     if (tri) { g.tri0 = 0; g.triT = cdiv(rows, FGP_TILE); }
     else { g.rectR0 = 0; g.rectNR = cdiv(rows, FGP_TILE); g.rectC0 = 0; g.rectNC = cdiv(cols, FGP_TILE); }
     g.rowMin = 0; g.rowLo = rows; g.rowHoleHi = rows; g.nrows = rows;

@@ -129,6 +129,7 @@ struct GemmArgs {
     int bLowerTri;                             // 1: B(c, k) = 0 for k > c (panel solve with inv(L_kk)): skip the zero half
     int maxTilesPerCta;                        // 0 = automatic; 1 = one tile per CTA (look-ahead: the panel stream must find a free SM quickly)
     int dbg;                                   // experiment switches, honoured only when built with -DFGP_GEMM_DEBUG
+    int tma;                                   // 1: operands by TMA (gemm_tma.cu), 0: per-thread cp.async (gemm_dmma.cu)
     int pdl;                                   // 1: programmatic dependent launch (the prologue overlaps the previous kernel's tail); 2: also
                                                // release the dependents at once (single-factorisation chain: the next kernel waits resident)
 };

@@ -103,6 +103,7 @@ struct fgp_ctx {
     int streams = 8;
     int fit_workers = 8;      // fgp_fit_batch, fit_mode 0: concurrent candidate fits (host threads) per GPU
     int fit_mode = 1;         // 1: lock-step -- one host thread per GPU advances all in-flight candidates together (fitlock.cu); 0: one thread per candidate
+    int gemm_tma = 1;         // operands of the DMMA GEMM by TMA (gemm_tma.cu); 0 = cp.async kernel
     int pdl = 1;              // programmatic dependent launch along the factorisation's kernel chain
     int fused_assembly = 1;   // batched likelihood calls assemble the matrices of one structure with the batch-fused kernel
     int fit_points = 0;       // lock-step: likelihood points per round and lane (0 = by memory, at most 512)

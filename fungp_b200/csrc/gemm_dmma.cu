@@ -384,7 +384,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs g, 
 
 }  // namespace
 
+bool launch_gemm_tma(const GemmArgs& g, cudaStream_t st);
+
 void launch_gemm(const GemmArgs& g, cudaStream_t st) {
+    // TMA operand path (gemm_tma.cu): same numerics; falls back here when it cannot take the launch
+    if (g.tma && launch_gemm_tma(g, st)) return;
     static bool attr_set[FGP_MAXDEV] = {false};
     static int nsm[FGP_MAXDEV] = {0};
     int dev = 0;

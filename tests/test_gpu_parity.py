@@ -684,3 +684,35 @@ def test_batch_fused_assembly_is_bit_identical(ctx, ker):
             assert (a[2] == 0).all()
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), (n, B)
         P.close()
+
+
+def test_tma_and_cp_async_gemm_kernels_agree_bitwise(ctx):
+    """The DMMA GEMM with TMA-fed operands (csrc/gemm_tma.cu: 3-D tensor maps, one producer thread, [k][132]-pitch slabs) and
+    the cp.async kernel (csrc/gemm_dmma.cu) accumulate in the same order: likelihood, preMats, predict and simulate are
+    identical to the last bit -- ragged sizes, batches, the look-ahead path, prefactored tiles, rectangular products."""
+    seed, n, m = 71, 1333, 300
+    case = make_case(seed, n, 3, [30, 20], [4, 3], ["B-splines", "B-splines"], ["L2_bygroup", "L2_byindex"], extra=m)
+    P = _problem(ctx, case)
+    ub = 2.0 * P.dist_max()
+    theta = 0.3 * ub
+    th5 = np.stack([theta * (1 + 0.03 * i) for i in range(5)], axis=1)
+    Z = np.random.default_rng(seed).standard_normal((m, 7))
+    out = {}
+    try:
+        for tma in (0, 1):
+            ctx.set_option("gemm_tma", tma)
+            a = P.nll_batch("matern5_2", 1e-8, theta)
+            b = P.nll_batch("matern5_2", 1e-8, th5)
+            L, z = P.premats("matern5_2", 1e-8, a[1][0], theta)
+            pr = P.predict(m, case["sNew"], case["coefsNew"])
+            sm = P.simulate(m, Z, case["sNew"], case["coefsNew"], nugget_sm=1e-8)
+            q2 = P.loocv()[1]
+            out[tma] = (a[0], b[0], b[1], L, z, pr["mean"], pr["sd"], sm["sims"], np.array([q2]))
+    finally:
+        ctx.set_option("gemm_tma", 1)
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y)
+    Ms = oracle_dists(case)
+    r_nll, _ = ref.negLogLik(theta, [], Ms, case["y"], "matern5_2", 1e-8)
+    assert abs(out[1][0][0] - r_nll) <= _nll_tol(r_nll, n)
+    P.close()
