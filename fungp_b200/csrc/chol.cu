@@ -148,6 +148,33 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
         return entries * 2.0 * (double)g.K * t.batch;
     };
 
+    // Prefactored steps whose column range straddles the boundary between kept and new columns AND whose extra rows reach
+    // below the last column tile (fgp_premats_reuse with n a multiple of 128: the y row sits alone in tile ncT): the
+    // rectangle (rows below the triangle) x (new columns) is not part of make_update's one-rectangle region -- second launch
+    auto make_update_tail = [&](int kA, int K, const RowSet& S, int cLo, int cHi, GemmArgs& g) {
+        if (!(S.hi2 > S.lo2) || S.lo2 >= cHi || cLo >= S.lo2 || S.hi2 <= cHi) return false;
+        g = base;
+        g.A = t.M + (long)kA * NBk * t.ld;
+        g.B = g.A;
+        g.C = t.M;
+        g.K = K; g.accumulate = 1; g.bTileBase = 0;
+        g.tri0 = 0; g.triT = 0; g.rectR0 = 0; g.rectNR = 0;
+        g.rectR1 = cHi; g.rectNR1 = S.hi2 - cHi;
+        g.rectC0 = S.lo2; g.rectNC = cHi - S.lo2;
+        return true;
+    };
+    auto launch_update = [&](int kA, int K, const RowSet& S, int cLo, int cHi, cudaStream_t st, bool timed) {
+        GemmArgs g = make_update(kA, K, S, cLo, cHi);
+        if (timed && tm) tm->begin(st);
+        launch_gemm(g, st);
+        if (timed && tm) tm->end(st, FgpTimers::UPDATE, flops_of(g));
+        GemmArgs g2;
+        if (make_update_tail(kA, K, S, cLo, cHi, g2)) {
+            if (timed && tm) tm->begin(st);
+            launch_gemm(g2, st);
+            if (timed && tm) tm->end(st, FgpTimers::UPDATE, flops_of(g2));
+        }
+    };
     int k = 0;
     while (k < ncT) {
         // ---- outer panel [k, kend): never straddles the prefactored boundary or the column hole
@@ -165,12 +192,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
                 factor_range(a, mid);
                 int Kl = 0;
                 for (int kk = a; kk < mid; ++kk) Kl += std::max(0, col_nb(kk));
-                if (Kl > 0) {
-                    GemmArgs g = make_update(a, Kl, rows_of(mid - 1), mid, b);
-                    if (tm) tm->begin(sPanel);
-                    launch_gemm(g, sPanel);
-                    if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
-                }
+                if (Kl > 0) launch_update(a, Kl, rows_of(mid - 1), mid, b, sPanel, true);
                 factor_range(mid, b);
                 return;
             }
@@ -213,10 +235,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
         if (kend < ncT && Kpanel > 0) {
             const RowSet S = rows_of(kend - 1);
             if (!la) {
-                GemmArgs g = make_update(k, Kpanel, S, kend, ncT);
-                if (tm) tm->begin(sPanel);
-                launch_gemm(g, sPanel);
-                if (tm) tm->end(sPanel, FgpTimers::UPDATE, flops_of(g));
+                launch_update(k, Kpanel, S, kend, ncT, sPanel, true);
             } else {
                 // look-ahead: the next panel's columns on the panel stream (critical path), the rest on the bulk stream
                 int kend2 = std::min(kend + width_at(kend), ncT);
@@ -224,10 +243,10 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
                 if (kend < colSegTile) kend2 = std::min(kend2, colSegTile);
                 cudaEventRecord(evPanel, sPanel);                           // panel solved
                 if (bulkPending) cudaStreamWaitEvent(sPanel, evBulk, 0);   // its columns carry the previous bulk update
-                launch_gemm(make_update(k, Kpanel, S, kend, kend2), sPanel);
+                launch_update(k, Kpanel, S, kend, kend2, sPanel, false);
                 if (kend2 < ncT) {
                     cudaStreamWaitEvent(sBulk, evPanel, 0);
-                    launch_gemm(make_update(k, Kpanel, S, kend2, ncT), sBulk);
+                    launch_update(k, Kpanel, S, kend2, ncT, sBulk, false);
                     cudaEventRecord(evBulk, sBulk);
                     bulkPending = true;
                 }
