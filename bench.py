@@ -363,12 +363,12 @@ def run_ours(args):
                     "this repo's sustained DMMA measurement on this pool (37.08, profiles/r01_peaks.md); the live loops gave %.2f" % live)
         # per-launch CUDA events (profile mode: one stream, two single evaluations) -- explains the step, is not the step
         ctx.set_option("profile", 1)
-        P.nll_batch(ker, nug, thetas[:, :2])
-        P.nll_batch(ker, nug, thetas[:, :2])
+        P.nll_batch(ker, nug, thetas)
+        P.nll_batch(ker, nug, thetas)
         tm = ctx.timing()
         ctx.set_option("profile", 0)
         upd_tf = tm["update_flops"] / (tm["update_ms"] * 1e-3) / 1e12
-        asm_bytes = 2 * 8.0 * n * (n + 1) / 2          # two matrices in the profiled call
+        asm_bytes = B * 8.0 * n * (n + 1) / 2          # the B matrices of the profiled call: one batch-fused assembly launch
         asm_gbs = asm_bytes / (tm["assembly_ms"] * 1e-3) / 1e9
         hbm_peak = None
         try:
@@ -406,25 +406,27 @@ def run_ours(args):
             "clocks": clocks,
             # achieved = ALGORITHMIC flops of the blocked Cholesky (n^3/3 per evaluation) over the timed step itself: assembly,
             # diagonal blocks, panel solves and reductions are all inside the time, so this can only understate the kernel
-            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (trailing update of the blocked Cholesky, FP64 DMMA m8n8k4) -- "
-                                                      "measured as the whole timed step",
+            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_tma_kernel (trailing update of the blocked Cholesky: FP64 DMMA m8n8k4, "
+                                                      "operands by TMA) -- measured as the whole timed step",
                          "achieved": step_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": step_tf / fp64_peak,
                          "flops_per_step_per_gpu": chol_flops * B,
                          "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": peak_src + "; MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = 37.2 TFLOP/s "
                                         "at 1965 MHz",
-                         "update_kernel_profiled": {"note": "per-launch CUDA events, one stream, two single evaluations (not the batched step); "
-                                                            "flops count the triangle of diagonal tiles",
+                         "update_kernel_profiled": {"note": "per-launch CUDA events, the step's 13 points as one batch on ONE stream (the timed step "
+                                                            "spreads them over 8); flops count the triangle of diagonal tiles",
                                                     "tflops": upd_tf, "frac": upd_tf / fp64_peak,
                                                     "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
                                                     "launch_ms_avg": tm["update_ms"] / max(1, tm["update_launches"])}},
             "single_eval": {"ms": single_ms, "tflops": chol_flops / (single_ms * 1e-3) / 1e12, "frac": chol_flops / (single_ms * 1e-3) / 1e12 / fp64_peak,
                             "note": "one fgp_nll_batch call with B = 1 (look-ahead schedule), host wall clock, mean of 5"},
-            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_kernel<gauss> (fused distance + correlation, lower triangle)",
+            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_fused_kernel<gauss> (distance + correlation, lower triangles of the "
+                                                            "step's 13 matrices in one launch)",
                                   "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
-                                  "algorithmic_bytes_per_launch": asm_bytes / 2, "launch_ms": tm["assembly_ms"] / 2,
+                                  "algorithmic_bytes_per_launch": asm_bytes, "launch_ms": tm["assembly_ms"],
+                                  "bytes_per_matrix": asm_bytes / B, "ms_per_matrix": tm["assembly_ms"] / B,
                                   "note": "FP64-issue bound: DMMA and DFMA share one datapath (DESIGN.md 2.3)"},
-            "kernel_ms_profiled_2evals": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
+            "kernel_ms_profiled_13evals_1stream": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
             "fp64_peaks_measured": peaks,
             "nll_check": float(nll_last[0]),
         }

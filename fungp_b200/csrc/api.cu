@@ -545,6 +545,26 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
         if (n < 2048) ns = 1;
         else if (n < 4096) ns = std::min(ns, 2);
         const int per = cdiv(cb, ns);
+        // The points of a batch share every coordinate difference: with enough of them ONE batch-fused assembly launch
+        // builds all matrices of the chunk (bit-identical entries) on the first stream, and the groups fork from there;
+        // otherwise every group assembles its own matrices on its stream.
+        const bool fuseAll = cb >= 4 && ctx->fused_assembly && assemble_fusable(nt, (int)P->units.size());
+        auto enqueue_front = [&]() -> int {
+            cudaStream_t st = d.sPanel[0];
+            CK(cudaMemcpyAsync(dScale, hScale, sizeof(double) * (size_t)cb * nt, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(dInfo, 0, sizeof(int) * cb, st));
+            if (var_known) CK(cudaMemcpyAsync(dVar, &hVar, sizeof(double), cudaMemcpyHostToDevice, st));
+            AsmArgs a = fgp_train_asm(P, pd, ker, dScale);
+            a.diag_rel = nugget; a.M = (double*)d.work.p; a.ld = ld; a.strideM = (long)ld * n;
+            if (prof) d.timers.begin(st);
+            launch_assemble_fused(a, nullptr, 1, cb, st);
+            if (prof) d.timers.end(st, FgpTimers::ASSEMBLY, 0.0);
+            if (ns > 1) {
+                CK(cudaEventRecord(d.evA, st));
+                for (int s = 1; s < ns; ++s) CK(cudaStreamWaitEvent(d.sPanel[s], d.evA, 0));
+            }
+            return 0;
+        };
         // one group = one launch sequence on its stream
         auto enqueue_group = [&](int s) -> int {
             const int g0 = s * per, g1 = std::min(cb, g0 + per);
@@ -552,17 +572,17 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             const int gb = g1 - g0;
             cudaStream_t st = d.sPanel[s];
             double* Mg = (double*)d.work.p + (size_t)g0 * ld * n;
-            CK(cudaMemcpyAsync(dScale + (size_t)g0 * nt, hScale + (size_t)g0 * nt, sizeof(double) * (size_t)gb * nt,
-                               cudaMemcpyHostToDevice, st));
-            CK(cudaMemsetAsync(dInfo + g0, 0, sizeof(int) * gb, st));
-            if (var_known) CK(cudaMemcpyAsync(dVar, &hVar, sizeof(double), cudaMemcpyHostToDevice, st));
-            AsmArgs a = fgp_train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
-            a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
-            if (prof) d.timers.begin(st);
-            // the points of a batch share every coordinate difference: one batch-fused launch (bit-identical entries)
-            if (gb >= 4 && ctx->fused_assembly && assemble_fusable(nt, (int)P->units.size())) launch_assemble_fused(a, nullptr, 1, gb, st);
-            else launch_assemble(a, gb, st);
-            if (prof) d.timers.end(st, FgpTimers::ASSEMBLY, 0.0);
+            if (!fuseAll) {
+                CK(cudaMemcpyAsync(dScale + (size_t)g0 * nt, hScale + (size_t)g0 * nt, sizeof(double) * (size_t)gb * nt,
+                                   cudaMemcpyHostToDevice, st));
+                CK(cudaMemsetAsync(dInfo + g0, 0, sizeof(int) * gb, st));
+                if (var_known) CK(cudaMemcpyAsync(dVar, &hVar, sizeof(double), cudaMemcpyHostToDevice, st));
+                AsmArgs a = fgp_train_asm(P, pd, ker, dScale + (size_t)g0 * nt);
+                a.diag_rel = nugget; a.M = Mg; a.ld = ld; a.strideM = (long)ld * n;
+                if (prof) d.timers.begin(st);
+                launch_assemble(a, gb, st);
+                if (prof) d.timers.end(st, FgpTimers::ASSEMBLY, 0.0);
+            }
             launch_fill_yrow(Mg, ld, (long)ld * n, gb, n, pd.y, n, st);
             TrapDesc t{};
             t.M = Mg; t.ld = ld; t.strideM = (long)ld * n; t.batch = gb;
@@ -599,7 +619,8 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
                 if (!gr->exec) {
                     cudaGraph_t graph = nullptr;
                     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    const int rce = enqueue_group(0);
+                    int rce = fuseAll ? enqueue_front() : 0;
+                    if (!rce) rce = enqueue_group(0);
                     cudaError_t ec = cudaMemcpyAsync(hRes, dNll, resBytes, cudaMemcpyDeviceToHost, st);
                     cudaError_t ee = cudaStreamEndCapture(st, &graph);
                     if (rce || ec != cudaSuccess || ee != cudaSuccess || !graph) {
@@ -619,11 +640,13 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
                 }
             }
         }
-        if (!replayed)
+        if (!replayed) {
+            if (fuseAll && (rc = enqueue_front())) return rc;
             for (int s = 0; s < ns; ++s) {
                 rc = enqueue_group(s);
                 if (rc) return rc;
             }
+        }
         // join the groups on stream 0, fetch nll | sig2 | info with one copy, and wait once
         for (int s = 1; s < ns; ++s) {
             if (!d.evJoin[s]) CK(cudaEventCreateWithFlags(&d.evJoin[s], cudaEventDisableTiming));

@@ -186,8 +186,10 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap
                 for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) {
-                        acc[mi][ni][0] = Cw[mi * 8 + (long)(ni * 8) * g.ldc];
-                        acc[mi][ni][1] = Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc];
+                        // streaming loads / stores: a C tile is touched once per launch and must not push the operand
+                        // panel, which every tile row and column re-reads, out of L2
+                        acc[mi][ni][0] = __ldcs(&Cw[mi * 8 + (long)(ni * 8) * g.ldc]);
+                        acc[mi][ni][1] = __ldcs(&Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc]);
                     }
             } else {
 #pragma unroll
@@ -278,8 +280,8 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap
                 for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi) {
-                        Cw[mi * 8 + (long)(ni * 8) * g.ldc] = acc[mi][ni][0];
-                        Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc] = acc[mi][ni][1];
+                        __stcs(&Cw[mi * 8 + (long)(ni * 8) * g.ldc], acc[mi][ni][0]);
+                        __stcs(&Cw[mi * 8 + (long)(ni * 8 + 1) * g.ldc], acc[mi][ni][1]);
                     }
             } else {
 #pragma unroll
