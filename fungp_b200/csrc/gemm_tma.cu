@@ -93,11 +93,12 @@ __device__ __forceinline__ TileId decode_tile(const GemmArgs& g, int t) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int nitems, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const long b = blockIdx.y;
     const int nchunks = (g.K + KC - 1) / KC;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t fullB = sbase + SMEM_BYTES;            // full[s]  at +8 s
@@ -114,17 +115,17 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int nitems, const __grid_constant__
     // programmatic dependent launch: everything above overlapped the previous kernel's tail
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     if (g.pdl == 2) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    // Work items = (tile, batch element) pairs, tile-major inside a batch element: a CTA walks items w, w + gridDim.x, ...
-    // of the WHOLE launch, so the operand ring and the C prefetch run through tile AND matrix boundaries.  (With one
-    // grid row per batch element a small-n launch -- 8 tiles x 400 matrices -- was 3200 one-tile CTAs, each paying the
-    // cold pipeline fill.)
-    int w = blockIdx.x;
-    if (w >= nitems) return;
+    // (Tried: one 1-D grid over all (tile, batch element) pairs, so that the ring also runs through matrix boundaries of
+    // small-n batches.  Measured 4 % slower at n = 1024 x 60 -- tiles differ in cost (one-row y tiles, diagonal tiles) and
+    // many short CTAs balance better than few long ones -- and no different at n = 8192; one grid row per batch element stays.)
+    int tIdx = blockIdx.x;
+    if (tIdx >= ntiles) return;
     const Valid rv{g.rowMin, g.rowLo, g.rowHoleHi, g.nrows};
     const Valid cv{g.colMin, g.colLo, g.colHoleHi, g.ncols};
     // warps (wm, wn): 4 along m (32 rows each) x 2 along n (64 cols each); same assignment as gemm_dmma_kernel
     const int wn = (warp >> 2) & 1;
     const int wm = (warp + wn) & 3;
+    double* C = g.C + b * g.strideC;
     const int sgnmask = g.accumulate ? (int)0x80000000 : 0;   // C -= A B': flip the sign bit of the A fragments (integer op)
     const int r_lane = lane >> 2;        // row within an 8x8 DMMA tile
     const int c_lane = 2 * (lane & 3);   // first of the two columns this lane owns
@@ -136,23 +137,20 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int nitems, const __grid_constant__
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s) {
             const int off = s / nchunks, cn = s - off * nchunks;
-            const int tgt = w + off * (int)gridDim.x;
-            if (tgt < nitems) {
-                const int tb = tgt / ntiles;
-                const TileId t1 = decode_tile(g, tgt - tb * ntiles);
+            const int tgt = tIdx + off * (int)gridDim.x;
+            if (tgt < ntiles) {
+                const TileId t1 = decode_tile(g, tgt);
                 mbar_expect_tx(fullB + 8 * s, STAGE_TX);
                 const uint32_t dst = sbase + (uint32_t)(s * STAGE * 8);
-                tma_load_3d(dst, &mapA, fullB + 8 * s, t1.I * FGP_TILE, cn * KC, tb);
-                tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * s, (t1.J - g.bTileBase) * FGP_TILE, cn * KC, tb);
+                tma_load_3d(dst, &mapA, fullB + 8 * s, t1.I * FGP_TILE, cn * KC, (int)b);
+                tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * s, (t1.J - g.bTileBase) * FGP_TILE, cn * KC, (int)b);
             }
         }
     }
 
     int gc = 0;   // global chunk counter of this CTA (ring position)
-    for (; w < nitems; w += gridDim.x) {
-        const int b = w / ntiles;
-        const TileId tl = decode_tile(g, w - b * ntiles);
-        double* C = g.C + (long)b * g.strideC;
+    for (; tIdx < ntiles; tIdx += gridDim.x) {
+        const TileId tl = decode_tile(g, tIdx);
         const int rowBase = tl.I * FGP_TILE;
         const int colBase = (tl.J - g.bTileBase) * FGP_TILE;
         const int wrow = rowBase + wm * 32;
@@ -215,13 +213,12 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int nitems, const __grid_constant__
             const int ahead = c + STAGES - 1;
             const int off = ahead / nchunks;
             const int cn = ahead - off * nchunks;
-            const int tgt = w + off * (int)gridDim.x;
-            const bool doCopy = tgt < nitems;
-            const int tb = doCopy ? tgt / ntiles : b;
+            const int tgt = tIdx + off * (int)gridDim.x;
+            const bool doCopy = tgt < ntiles;
             if (off > 0 && doCopy && cn == 0 && g.accumulate) {
                 // pull that tile's C into L2: 128 columns x 8 lines of 128 bytes, 4 lines per thread
-                const TileId t1 = decode_tile(g, tgt - tb * ntiles);
-                const double* Cn = g.C + (long)tb * g.strideC + (long)t1.I * FGP_TILE + (long)((t1.J - g.bTileBase) * FGP_TILE) * g.ldc;
+                const TileId t1 = decode_tile(g, tgt);
+                const double* Cn = C + (long)t1.I * FGP_TILE + (long)((t1.J - g.bTileBase) * FGP_TILE) * g.ldc;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int q = tid + THREADS * i;
@@ -244,13 +241,13 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int nitems, const __grid_constant__
                     if (gc + STAGES - 1 >= STAGES) mbar_wait(emptyB + 8 * sn, (((gc + STAGES - 1) / STAGES) - 1) & 1);
                     int rb = rowBase, cb = colBase;
                     if (off > 0) {
-                        const TileId t1 = decode_tile(g, tgt - tb * ntiles);
+                        const TileId t1 = decode_tile(g, tgt);
                         rb = t1.I * FGP_TILE; cb = (t1.J - g.bTileBase) * FGP_TILE;
                     }
                     mbar_expect_tx(fullB + 8 * sn, STAGE_TX);
                     const uint32_t dst = sbase + (uint32_t)(sn * STAGE * 8);
-                    tma_load_3d(dst, &mapA, fullB + 8 * sn, rb, cn * KC, tb);
-                    tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * sn, cb, cn * KC, tb);
+                    tma_load_3d(dst, &mapA, fullB + 8 * sn, rb, cn * KC, (int)b);
+                    tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * sn, cb, cn * KC, (int)b);
                 }
                 if (mult) {
                     double a[4], bb[8];
@@ -356,22 +353,19 @@ bool launch_gemm_tma(const GemmArgs& g, cudaStream_t st) {
     const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
     int tpc = std::max(1, std::min(16, 3072 / std::max(1, g.K)));       // tiles per CTA: K=128 -> 16 ... K>=2048 -> 1
     if (g.maxTilesPerCta > 0) tpc = std::min(tpc, g.maxTilesPerCta);
-    // one 1-D grid over all (tile, batch element) items; whole waves when there are more CTAs than SMs
-    const long nitems = (long)ntiles * g.batch;
-    if (nitems > 0x7fffffffL) return false;
-    long gx = nitems;
+    int gx = ntiles;
     if (g.maxTilesPerCta != 1) {
-        const long want = (nitems + tpc - 1) / tpc;
-        gx = want <= sms ? std::min<long>(nitems, sms) : std::min<long>(nitems, ((want + sms - 1) / sms) * sms);
+        const int want = (ntiles + tpc - 1) / tpc;
+        gx = want <= sms ? std::min(ntiles, sms) : std::min(ntiles, ((want + sms - 1) / sms) * sms);
     }
     FGP_COUNT_LAUNCH();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)gx); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES + 64; cfg.stream = st;
+    cfg.gridDim = dim3(gx, g.batch); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES + 64; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g.pdl ? 1 : 0;
     GemmArgs gg = g;
-    if (gg.pdl == 2 && gx > sms) gg.pdl = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_dmma_tma_kernel, gg, ntiles, (int)nitems, mapA, mapB) == cudaSuccess;
+    if (gg.pdl == 2 && (long)gx * g.batch > sms) gg.pdl = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_dmma_tma_kernel, gg, ntiles, mapA, mapB) == cudaSuccess;
 }
