@@ -335,6 +335,16 @@ def run_ours(args):
                       "nll_batch_sharded_bit_identical": bool(np.array_equal(nllN[:B], nll_last) and np.array_equal(nllN[:B], nllN[-B:]))}
             ctxN.close()
         barrier()
+    # one 2d+1 batch split over the ranks and gathered on the host (fungp_b200/shard.py: the one-process-per-GPU analogue of
+    # the split fgp_nll_batch makes inside a multi-GPU context): must equal rank 0's own evaluation of the whole batch
+    sharded_ok = None
+    if world > 1:
+        from fungp_b200 import shard
+        th0 = synth.fd_points(CFG["theta_frac"] * ub, np.full(d, 1e-10), ub)
+        sn, ss, si = shard.sharded_nll(P, ker, nug, th0, rank, world)
+        if rank == 0:
+            fn, fs, fi = P.nll_batch(ker, nug, th0)
+            sharded_ok = bool(np.array_equal(sn, fn) and np.array_equal(ss, fs) and np.array_equal(si, fi))
     total_evals = world * B * args.steps
     # the step ends with a host-synchronous read of its results, so wall time >= device time; report the wall clock
     value = total_evals / wall
@@ -430,6 +440,8 @@ def run_ours(args):
             "fp64_peaks_measured": peaks,
             "nll_check": float(nll_last[0]),
         }
+        if sharded_ok is not None:
+            out["sharded_batch_bit_identical"] = sharded_ok
         if fac is not None:
             nf = FACTORY["n"]
             agg_flops = fac["nll_evals"] * nf ** 3 / 3.0 + fac["loocv"] * 2.0 * nf ** 3 / 3.0

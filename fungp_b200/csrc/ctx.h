@@ -107,7 +107,7 @@ struct fgp_ctx {
     int pdl = 1;              // programmatic dependent launch along the factorisation's kernel chain
     int fused_assembly = 1;   // batched likelihood calls assemble the matrices of one structure with the batch-fused kernel
     int fit_points = 0;       // lock-step: likelihood points per round and lane (0 = by memory, at most 512)
-    int fit_lanes = 0;        // lock-step: rounds in flight per GPU (0 = 2 below n = 2048, else 1)
+    int fit_lanes = 0;        // lock-step: rounds in flight per GPU (0 = 3 below n = 2048, else 1)
     int predict_reserve = 2048;   // rows kept free under the stored factor so that predict / simulate solve in place
     int graphs = 0;           // option "graphs": replay small-n likelihood calls as CUDA graphs (second call onwards)
     int blockingSync = 0;     // host waits sleep instead of spinning (set on fit_batch worker contexts)

@@ -82,8 +82,8 @@ def r_fd_points(x, lower, upper, ndeps=1e-3):
 def optim_lbfgsb_batched(nll_batch, x0, lower, upper, maxit=100, factr=1e7, pgtol=0.0, lmm=5):
     """L-BFGS-B with R's control defaults (R/3_training_SF.R:125; optim: lmm 5, factr 1e7, pgtol 0, maxit 100) and R's
     finite-difference gradient, value and gradient coming from one batched device call per iterate.
-    nll_batch(points d x B) -> nll[B]; raises NotPosDefError when the value at the iterate itself is not computable
-    (R would stop inside fn), finite-difference neighbours that fail make the fit fail the same way."""
+    nll_batch(points d x B) -> nll[B]; it raises NotPosDefError when the iterate or any of its finite-difference neighbours
+    cannot be evaluated (R would stop inside fn / gr), which the caller treats as a lost start."""
     from scipy.optimize import minimize
     lower = np.asarray(lower, dtype=np.float64); upper = np.asarray(upper, dtype=np.float64)
 
@@ -195,9 +195,13 @@ def fgpm(sIn=None, fIn=None, sOut=None, kerType="matern5_2", f_disType="L2_bygro
         for i in range(n_starts):                                  # optimHypers_*, R/3_training_SF.R:122-223
             try:
                 def nb(pts):
+                    # any point of the finite-difference batch that cannot be evaluated is an error inside optim(): the start
+                    # is lost (tryCatch below), exactly as in fitbatch.cu / fitlock.cu and in R
                     v, _, info = P.nll_batch(kerType, nugget, full_theta(pts), var_known=var_hyp)
-                    if info[0]:
-                        raise NotPosDefError(int(info[0]))
+                    if info.any():
+                        raise NotPosDefError(int(info[np.nonzero(info)[0][0]]))
+                    if not np.all(np.isfinite(v)):
+                        raise ValueError("non-finite likelihood")
                     return v
                 x, f, conv = optim_lbfgsb_batched(nb, sp[:, i], lower, upper)
             except (NotPosDefError, ValueError):

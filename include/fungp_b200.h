@@ -158,7 +158,7 @@ int fgp_loocv(fgp_problem* prob, double* y_pre, double* q2);
  * in-flight candidates together; every round the pending likelihood points of all of them (presample points,
  * finite-difference points of an L-BFGS-B iterate, the value at the optimum) form one heterogeneous batched launch
  * sequence, and the leave-one-out factorisations of the candidates that finished are batched the same way; options
- * "fit_points" (points per round and lane, default 512 or what memory allows) and "fit_lanes" (rounds in flight per GPU).
+ * "fit_points" (points per round and lane, default 1024 or what memory allows) and "fit_lanes" (rounds in flight per GPU).
  * 0 = one host thread per candidate, `fit_workers` (option, default 8) of them per GPU, each with its own streams and
  * workspaces.  Per-item results do not depend on the mode, the options or the number of GPUs; GPUs exchange nothing.
  * A failure of the library itself (CUDA error, out of memory) is returned as the call's error code, not reported as
