@@ -33,6 +33,14 @@ if "c2" in which:
     pr = M.predict(mod, sIn_pr=sIn[n:], fIn_pr=[f[n:] for f in fIn])
     t_pr = tic() - t0
     rmse = float(np.sqrt(np.mean((pr["mean"] - y[n:]) ** 2)))
+    # the same fit with all 10 starts advanced together by the lock-step driver (one candidate = the full structure)
+    from fungp_b200 import factory as F
+    ant = F.encode_ant(2, 2, [0, 1], [0, 1], ["L2_bygroup"] * 2, [5, 5], ["B-splines"] * 2, "matern5_2")
+    F.score_candidates(ctx, sIn[:n], [f[:n] for f in fIn], y[:n], ant[None, :], M.NumpyRng(1), n_starts=10, n_presample=20)
+    t0 = tic()
+    rl = F.score_candidates(ctx, sIn[:n], [f[:n] for f in fIn], y[:n], ant[None, :], M.NumpyRng(1), n_starts=10, n_presample=20)
+    t_lock = tic() - t0
+    out["c2_lockstep"] = dict(fit_and_q2_seconds=t_lock, nll=float(rl["nll"][0]), q2=float(rl["fitness"][0]))
     out["c2"] = dict(n=n, m=m, fit_seconds=t_fit, predict_seconds=t_pr, nll=mod.negLogLik, sig2=mod.kern.varHyp,
                      ls=np.r_[mod.kern.s_lsHyps, mod.kern.f_lsHyps].tolist(), rmse=rmse, sd_range=[float(pr["sd"].min()), float(pr["sd"].max())],
                      kernel_launches=ctx.launch_count())
@@ -52,10 +60,16 @@ if "c3" in which:
     t0 = tic(); P.premats("gauss", 1e-8, s2[0], theta, want_L=False); t_pm = tic() - t0
     t0 = tic(); pr = P.predict(m, sIn[n:], cnew); t_pr = tic() - t0
     Z = np.random.default_rng(1).standard_normal((m, nsim))
+    P.predict(m, sIn[n:], cnew); t0 = tic(); pr = P.predict(m, sIn[n:], cnew); t_pr = tic() - t0
+    P.simulate(m, Z, sIn[n:], cnew, nugget_sm=1e-8)          # warm: workspaces
     t0 = tic(); sm = P.simulate(m, Z, sIn[n:], cnew, nugget_sm=1e-8); t_sm = tic() - t0
+    t0 = tic(); Lh, zh = P.premats("gauss", 1e-8, s2[0], theta, want_L=True); t_pmL = tic() - t0
+    t0 = tic(); prf = P.predict(m, sIn[n:], cnew, detail="full"); t_prf = tic() - t0
     # properties: simulate's mean/sd equal predict's; the sample spread follows the predictive sd
     emp_sd = sm["sims"].std(axis=0)
     out["c3"] = dict(n=n, m=m, nsim=nsim, nll_seconds=t_nll, premats_seconds=t_pm, predict_seconds=t_pr, simulate_seconds=t_sm,
+                     premats_with_L_out_seconds=t_pmL, L_out_GBps=8.0 * n * n / max(t_pmL - t_pm, 1e-9) / 1e9,
+                     predict_full_seconds=t_prf, Ktp_Kpp_GBps=8.0 * (n * m + m * m) / max(t_prf - t_pr, 1e-9) / 1e9,
                      nll=float(nll[0]), mean_diff=float(np.max(np.abs(sm["mean"] - pr["mean"]))), sd_diff=float(np.max(np.abs(sm["sd"] - pr["sd"]))),
                      emp_vs_pred_sd_ratio_median=float(np.median(emp_sd / np.maximum(pr["sd"], 1e-12))),
                      rmse=float(np.sqrt(np.mean((pr["mean"] - y[n:]) ** 2))))
@@ -75,9 +89,12 @@ if "c5" in which:
     P.nll_batch("matern3_2", 1e-8, theta)
     t0 = tic(); nll, s2, info = P.nll_batch("matern3_2", 1e-8, theta); t_nll = tic() - t0
     t0 = tic(); P.premats("matern3_2", 1e-8, s2[0], theta, want_L=False); t_pm = tic() - t0
-    t0 = tic(); pr = P.predict(m, sIn[n:], cnew); t_pr1 = tic() - t0     # first call: the 9 GB workspace is (re)allocated
+    t0 = tic(); pr = P.predict(m, sIn[n:], cnew); t_pr1 = tic() - t0
     t0 = tic(); pr = P.predict(m, sIn[n:], cnew); t_pr = tic() - t0
-    out["c5"] = dict(n=n, m=m, distmax_seconds=t_dm, nll_seconds=t_nll, chol_tflops=n ** 3 / 3 / t_nll / 1e12, premats_seconds=t_pm,
+    t0 = tic(); Lh, zh = P.premats("matern3_2", 1e-8, s2[0], theta, want_L=True); t_pmL = tic() - t0
+    del Lh
+    out["c5"] = dict(n=n, m=m, premats_with_L_out_seconds=t_pmL, L_out_seconds=t_pmL - t_pm, L_out_GBps=8.0 * n * n / max(t_pmL - t_pm, 1e-9) / 1e9,
+                     distmax_seconds=t_dm, nll_seconds=t_nll, chol_tflops=n ** 3 / 3 / t_nll / 1e12, premats_seconds=t_pm,
                      predict_first_call_seconds=t_pr1, predict_seconds=t_pr, predict_trsm_tflops=float(n) * n * m / t_pr / 1e12, nll=float(nll[0]), info=int(info[0]),
                      rmse=float(np.sqrt(np.mean((pr["mean"] - y[n:]) ** 2))), sd_max=float(pr["sd"].max()))
     print("c5", out["c5"], flush=True)
