@@ -104,8 +104,12 @@ def optim_lbfgsb_batched(nll_batch, x0, lower, upper, maxit=100, factr=1e7, pgto
 
 def fgpm(sIn=None, fIn=None, sOut=None, kerType="matern5_2", f_disType="L2_bygroup", f_pdims=3, f_basType="B-splines",
          var_hyp=None, ls_s_hyp=None, ls_f_hyp=None, nugget=1e-8, n_starts=1, n_presample=20, rng=None, spoints_usr=None,
-         ctx=None, want_L=True, reuse=None):
+         ctx=None, want_L=True, reuse=None, optimizer="host"):
     """fgpm() (R/1_fgpm_Class.R:345-585): projection -> device problem -> setHypers_* -> preMats_*.
+    optimizer: "host" drives scipy's L-BFGS-B from this process, one batched device call per iterate (the role stats::optim
+    keeps in the R package); "lockstep" hands the whole multistart fit to the library's own L-BFGS-B (fgp_fit_batch with this
+    structure as its only candidate): all n_starts starts advance together, one launch sequence per round -- available when
+    no hyper-parameter is given and no user start points are.  Same presample draws from `rng` either way.
     reuse: a fitted model whose factor may be re-used (update() fast path): honoured when every hyper-parameter is given
     and the length-scales, kernel and nugget are those of `reuse` -- the leading points both data sets share keep their
     block of the factor (fgp_premats_reuse), a different variance is applied by rescaling (fgp_update_var)."""
@@ -183,7 +187,26 @@ def fgpm(sIn=None, fIn=None, sOut=None, kerType="matern5_2", f_disType="L2_bygro
             return v
 
         # setSPoints_*, R/3_training_SF.R:83-108: ONE batched call for the n.presample points
-        u = np.asarray(rng.runif(free.size * n_presample)).reshape((n_presample, free.size)).T
+        u_flat = np.asarray(rng.runif(free.size * n_presample))
+        if optimizer == "lockstep" and s_free == (d_s > 0) and f_free == (d_f > 0) and var_hyp is None and spoints_usr is None:
+            from . import factory as F
+            ant = F.encode_ant(m.ds, m.df, list(range(m.ds)), list(range(m.df)), dis, pdims if m.df else [],
+                               [b if b in BASIS else "B-splines" for b in bas] if m.df else [], kerType)
+            r = ctx.fit_batch(m.sIn, m.fIn, y, ant[None, :], [u_flat], nugget=nugget, n_starts=n_starts, n_presample=n_presample,
+                              dmax=P.d)
+            if r["info"][0] > 0:
+                raise NotPosDefError(int(r["info"][0]))
+            if r["info"][0] < 0:
+                raise RuntimeError("All model optimizations crashed!")
+            theta = r["theta"][0][:P.d].copy()
+            m.negLogLik, m.convergence = float(r["nll"][0]), 0.0
+            m.kern.varHyp = float(r["sig2"][0])
+            m.kern.s_lsHyps, m.kern.f_lsHyps = theta[:d_s].copy(), theta[d_s:].copy()
+            m.reused_points = 0
+            L, z = P.premats(kerType, nugget, m.kern.varHyp, theta, want_L=want_L)
+            m.preMats = dict(L=L, LInvY=z)
+            return m
+        u = u_flat.reshape((n_presample, free.size)).T
         allsp = lower[:, None] + u * (upper - lower)[:, None]
         fit = nll_pts(allsp, strict=True)
         sp = allsp[:, np.argsort(fit, kind="stable")[:n_starts]].copy()

@@ -166,6 +166,14 @@ def test_scores_vs_oracle_at_the_fitted_hypers(ctx):
     loo = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20)
     hout = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20, ind_vl=ind_vl)
     assert (loo["info"] == 0).all() and (hout["info"] == 0).all()
+    try:        # the hold-out items through the one-thread-per-candidate driver: bit-identical (same schedule with look-ahead off)
+        ctx.set_option("fit_mode", 0); ctx.set_option("lookahead", 0)
+        hout0 = F.score_candidates(ctx, sIn, fIn, y, ants, RRng(3), n_starts=2, n_presample=20, ind_vl=ind_vl)
+    finally:
+        ctx.set_option("fit_mode", 1); ctx.set_option("lookahead", 1)
+    for key in ("nll", "sig2", "theta", "info"):
+        assert np.array_equal(hout0[key], hout[key], equal_nan=True), key
+    assert np.max(np.abs(hout0["fitness"] - hout["fitness"])) <= 1e-12      # preMats of the final stage: look-ahead on vs off
     for c, ant in enumerate(ants):
         kw = F.decode_ant(ant, ds, 2)
         nsA = len(kw["s_active"])

@@ -257,3 +257,28 @@ def test_saved_model_restores_and_predicts_identically(ctx):
         assert np.max(np.abs(pr["sd"] - po["sd"])) <= 1e-8 * np.sqrt(gm["varHyp"]) + 1e-8 * np.max(po["sd"]), name
         assert abs(Pm.loocv()[1] - gm["fitness"]) <= 1e-8, name
         Pm.close()
+
+
+def test_lockstep_optimizer_option_matches_host_optimizer(ctx):
+    """fgpm(optimizer="lockstep"): the whole multistart fit inside the library (all starts advanced together) against the
+    host-driven fit (scipy's L-BFGS-B, one batched call per iterate) and the oracle's fit, same R-compatible presample
+    stream: the same optimum to optimiser tolerance, identical presample consumption of the RNG."""
+    from fungp_b200 import model as M
+    n = 400
+    sIn, fIn, y, _ = synth_problem(85, n, 2, [30, 40])
+    kw = dict(kerType="matern5_2", f_disType=["L2_bygroup", "L2_byindex"], f_pdims=[4, 2], f_basType=["B-splines", "B-splines"],
+              nugget=1e-8, n_starts=4, n_presample=20)
+    r1, r2 = RRng(5), RRng(5)
+    gh = M.fgpm(sIn=sIn, fIn=fIn, sOut=y, rng=r1, ctx=ctx, **kw)
+    gl = M.fgpm(sIn=sIn, fIn=fIn, sOut=y, rng=r2, ctx=ctx, optimizer="lockstep", **kw)
+    assert r1.runif(1)[0] == r2.runif(1)[0]                         # both consumed the same number of draws
+    o = ref.fgpm(sIn=sIn, fIn=fIn, sOut=y, rng=RRng(5), **kw)
+    for g in (gh, gl):
+        assert abs(g.negLogLik - o.negLogLik) <= 1e-6 * max(abs(o.negLogLik), n)
+    assert abs(gl.kern.varHyp - gh.kern.varHyp) <= 1e-3 * gh.kern.varHyp
+    # the stored model of the lock-step fit is the oracle's at its hyper-parameters
+    o2 = ref.fgpm(sIn=sIn, fIn=fIn, sOut=y, kerType=kw["kerType"], f_disType=kw["f_disType"], f_pdims=kw["f_pdims"],
+                  f_basType=kw["f_basType"], var_hyp=gl.kern.varHyp, ls_s_hyp=gl.kern.s_lsHyps, ls_f_hyp=gl.kern.f_lsHyps, nugget=1e-8)
+    assert np.max(np.abs(gl.preMats["L"] - o2.L)) <= 1e-9 * np.max(np.abs(o2.L))
+    assert abs(M.loocv_q2(gl) - ref.q2_loocv(o2)) <= 1e-8
+    gh.close(); gl.close()
