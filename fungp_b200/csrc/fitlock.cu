@@ -551,13 +551,18 @@ struct Driver {
             a.XP = arenaX; a.nP = n; a.ldP = n; a.XQ = arenaX; a.nQ = n; a.ldQ = n;
             a.ker = ker; a.sym = 1; a.mult = 1.0; a.diag_rel = S.nugget; a.diag_abs = 0.0;
             a.ld = ld; a.strideM = (long)ld * n;
+            FgpTimers* tm = wc->profile ? &wc->dev[0].timers : nullptr;
             if (groupEnd[ker] > groupEnd[ker - 1]) {
                 a.M = (double*)ln.work.p; a.elems = dE;                  // groups carry absolute slot numbers
+                if (tm) tm->begin(s0);
                 launch_assemble_fused(a, dG + groupEnd[ker - 1], groupEnd[ker] - groupEnd[ker - 1], 0, s0);
+                if (tm) tm->end(s0, FgpTimers::ASSEMBLY, 0.0);
             }
             if (kerEnd[ker] > fusedEnd[ker]) {
                 a.M = (double*)ln.work.p + (size_t)fusedEnd[ker] * ld * n; a.elems = dE + fusedEnd[ker];
+                if (tm) tm->begin(s0);
                 launch_assemble(a, kerEnd[ker] - fusedEnd[ker], s0);
+                if (tm) tm->end(s0, FgpTimers::ASSEMBLY, 0.0);
             }
         }
         // ---- factorisations: groups of slots on the lane's streams (one group below n = 2048)
@@ -728,8 +733,13 @@ int fit_lockstep(fgp_ctx* ctx, Shared& S, const std::vector<int>& order) {
             wc->fit_points = ctx->fit_points; wc->fit_lanes = ctx->fit_lanes; wc->predict_reserve = ctx->predict_reserve;
             wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma;
             wc->blockingSync = ctx->fit_blocking > 0 ? ctx->fit_blocking : 0;
+            // option "profile": per-launch CUDA events of this call's rounds on the first GPU (meaningful with fit_lanes = 1,
+            // where the rounds do not overlap); fgp_get_timing on the caller's context reports them
+            wc->profile = (ctx->profile && dI == 0) ? 1 : 0;
+            if (wc->profile) wc->dev[0].timers.reset();
             Driver drv(ctx, wc, S, order);
             rcs[dI] = drv.run();
+            if (wc->profile) { cudaDeviceSynchronize(); std::swap(ctx->dev[0].timers, wc->dev[0].timers); wc->profile = 0; }
             if (rcs[dI]) {
                 // leave no stream work behind and no item unreported
                 cudaDeviceSynchronize();
