@@ -138,6 +138,8 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "graphs")) ctx->graphs = value != 0;
     else if (!strcmp(name, "fit_workers")) ctx->fit_workers = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "fit_mode")) ctx->fit_mode = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "la_r8")) ctx->la_r8 = std::max(0, (int)value);
+    else if (!strcmp(name, "la_r4")) ctx->la_r4 = std::max(0, (int)value);
     else if (!strcmp(name, "pdl")) ctx->pdl = value != 0 ? 1 : 0;
     else if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value != 0 ? 1 : 0; g_plain_tma = ctx->gemm_tma; }
     else if (!strcmp(name, "fused_assembly")) ctx->fused_assembly = value != 0 ? 1 : 0;

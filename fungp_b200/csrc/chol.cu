@@ -50,8 +50,8 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
         if (k == 0) return 2;
         if (k < 6) return 4;
         if (r > 136) return 16;
-        if (r > 44) return 8;
-        if (r > 28) return 4;
+        if (r > ctx->la_r8) return 8;
+        if (r > ctx->la_r4) return 4;
         return 2;
     };
     (void)colHole;

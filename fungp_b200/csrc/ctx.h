@@ -37,6 +37,12 @@ struct FgpTimers {
             ms[r.cls] += t; cnt[r.cls] += 1.0; fl[r.cls] += r.flops;
         }
     }
+    FgpTimers() = default;
+    FgpTimers(const FgpTimers&) = delete;             // owns its events: movable, not copyable
+    FgpTimers& operator=(const FgpTimers&) = delete;
+    FgpTimers(FgpTimers&& o) noexcept { swap(o); }
+    FgpTimers& operator=(FgpTimers&& o) noexcept { swap(o); return *this; }
+    void swap(FgpTimers& o) { pool.swap(o.pool); recs.swap(o.recs); std::swap(used, o.used); std::swap(cur, o.cur); }
     ~FgpTimers() { for (auto e : pool) cudaEventDestroy(e); }
 };
 
@@ -113,6 +119,7 @@ struct fgp_ctx {
     int blockingSync = 0;     // host waits sleep instead of spinning (set on fit_batch worker contexts)
     int fit_blocking = -1;    // option "fit_blocking": worker contexts of fgp_fit_batch use blocking waits (-1 = auto)
     int outer = 16;           // column tiles per outer panel for batches (trailing update K = outer*128)
+    int la_r8 = 44, la_r4 = 28;   // adaptive look-ahead widths: 8 tiles while more than la_r8 remain, 4 while more than la_r4 (chol.cu)
     int outer_single = 0;     // same for a single factorisation with look-ahead; 0 = by size (chol.cu)
     double timing[8] = {0};
     std::mutex mu;

@@ -739,7 +739,7 @@ int fit_lockstep(fgp_ctx* ctx, Shared& S, const std::vector<int>& order) {
             if (wc->profile) wc->dev[0].timers.reset();
             Driver drv(ctx, wc, S, order);
             rcs[dI] = drv.run();
-            if (wc->profile) { cudaDeviceSynchronize(); std::swap(ctx->dev[0].timers, wc->dev[0].timers); wc->profile = 0; }
+            if (wc->profile) { cudaDeviceSynchronize(); ctx->dev[0].timers.swap(wc->dev[0].timers); wc->profile = 0; }
             if (rcs[dI]) {
                 // leave no stream work behind and no item unreported
                 cudaDeviceSynchronize();
