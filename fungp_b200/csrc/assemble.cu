@@ -104,8 +104,11 @@ __device__ __forceinline__ double exp_nonpos(double t, const double2* sTab) {
     const double2 T = sTab[k & 31];
     double res = fma(T.x, __dmul_rn(r, p), T.x);           // T_hi (1 + r p)
     res = __dadd_rn(res, T.y);
-    res = __hiloint2double(__double2hiint(res) + ((k >> 5) << 20), __double2loint(res));
-    return t < -708.0 ? 0.0 : res;
+    // below about -708.0002 the result would leave the normal range (the exponent is patched by integer addition): flush to
+    // zero.  Negative doubles order like their high words taken as unsigned integers; 0xC0862000 is the high word of -708.
+    const bool under = (unsigned)__double2hiint(t) > 0xC0862000u;
+    const int hi = __double2hiint(res) + ((k >> 5) << 20);
+    return __hiloint2double(under ? 0 : hi, under ? 0 : __double2loint(res));
 }
 
 // KER: 0 = raw distance of the (single) term, 1 gauss, 2 matern5_2, 3 matern3_2
@@ -158,7 +161,9 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
             const FgpUnit un = units[ub + tid];
             sCol[tid] = un.col;
             sFlag[tid] = (un.kind ? 1 : 0) | (un.last ? 2 : 0);
-            sScale[tid] = (KER == 0) ? 1.0 : scale[un.term];
+            const double sc = (KER == 0) ? 1.0 : scale[un.term];
+            // gauss: -theta^-2 / 2 multiplies the SQUARED difference, so the sum arrives as the argument of the exp
+            sScale[tid] = (KER == 1) ? __dmul_rn(-0.5, __dmul_rn(sc, sc)) : sc;
         }
         __syncthreads();
         // stage nc columns x 64 points of each side (coalesced along points)
@@ -190,9 +195,9 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                         else {
                             // explicit roundings (no contraction left to the compiler): assemble_fused_kernel repeats these
                             // operations one for one and must give the same bits
+                            if (KER == 1) { S[i][j] = fma(__dmul_rn(d, d), sc, S[i][j]); continue; }
                             const double av = __dmul_rn(d, sc);
-                            if (KER == 1) S[i][j] = fma(av, av, S[i][j]);
-                            else {
+                            {
                                 S[i][j] = __dadd_rn(S[i][j], av);
                                 if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
                                 else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
@@ -209,7 +214,6 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                         D2[i][j] = fma(d, d, D2[i][j]);
                     }
                 if (flag & 2) {
-                    const double sc2 = __dmul_rn(sc, sc);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                             const double d2 = D2[i][j];
                             D2[i][j] = 0.0;
                             if (KER == 0) S[i][j] = sqrt(d2);
-                            else if (KER == 1) S[i][j] = fma(d2, sc2, S[i][j]);
+                            else if (KER == 1) S[i][j] = fma(d2, sc, S[i][j]);
                             else {
                                 const double av = __dmul_rn(sqrt(d2), sc);
                                 S[i][j] = __dadd_rn(S[i][j], av);
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
         for (int i = 0; i < 4; ++i) {
             double r;
             if (KER == 0) r = S[i][j];
-            else if (KER == 1) r = exp_nonpos(__dmul_rn(-0.5, S[i][j]), sExp);
+            else if (KER == 1) r = exp_nonpos(S[i][j], sExp);
             else r = __dmul_rn(Pr[i][j], exp_nonpos(-S[i][j], sExp));
             if (KER != 0) {
                 if (diagTile && lr[i] == lc0 + j) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
@@ -318,7 +322,7 @@ template <int KER>
 __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
     __shared__ __align__(16) double sP[FCC][FR];
     __shared__ __align__(16) double sQ[FCC][FC];
-    __shared__ double sSc[FBCH][FNT], sSc2[FBCH][FNT];
+    __shared__ __align__(16) double sSc[FBCH][FNT];   // gauss: -scale^2 / 2 (multiplies squared differences); Matern: scale
     __shared__ int sCol[FCC], sFlag[FCC], sTermFirst[FNT + 1], sNterms;
     __shared__ double2 sExp[32];
     load_exp_table(sExp);
@@ -365,7 +369,6 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
 
     // ---- base quantity of every term: |x_i - x_j|, or the summed squares (gauss) / their root (Matern) of a group
     double q[4][FNT];
-    unsigned groupMask = 0;
 #pragma unroll
     for (int t = 0; t < FNT; ++t) {
 #pragma unroll
@@ -377,8 +380,11 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
                 const double2 p23 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx + 2]);
                 const double xq = sQ[u0][ty];
                 q[0][t] = fabs(p01.x - xq); q[1][t] = fabs(p01.y - xq); q[2][t] = fabs(p23.x - xq); q[3][t] = fabs(p23.y - xq);
+                if (KER == 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i][t] = __dmul_rn(q[i][t], q[i][t]);
+                }
             } else {
-                groupMask |= 1u << t;
                 double D2[4] = {0.0, 0.0, 0.0, 0.0};
                 for (int u = u0; u < u1; ++u) {
                     const double2 p01 = *reinterpret_cast<const double2*>(&sP[u][4 * tx]);
@@ -395,6 +401,12 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
 
     const bool scaled = a.mult != 1.0;
     const int gi0 = i0 + 4 * tx, gj = j0 + ty;
+    // which of this thread's four entries lies on the diagonal of the matrix (0..3; anything else: none)
+    const unsigned dgi = (unsigned)((a.colOff + gj) - (a.rowOff + gi0));
+    const long colOffset = (long)(a.colOff + gj) * a.ld + a.rowOff + gi0;
+    // 16-byte stores need an aligned address in every matrix of the group: an even stride keeps the alignment of the first
+    const bool full4 = gi0 + 3 < a.nP && !(a.strideM & 1) &&
+                       ((reinterpret_cast<uintptr_t>(a.M + (long)g.first * a.strideM + colOffset) & 15) == 0);
     for (int b0 = 0; b0 < g.count; b0 += FBCH) {
         const int nb = min(FBCH, g.count - b0);
         __syncthreads();
@@ -405,53 +417,55 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
                 const double* scale = a.elems ? a.elems[g.first + b0 + b].scale : a.scale + (long)(g.first + b0 + b) * a.nterms;
                 sc = scale[t];
             }
-            sSc[b][t] = sc;
-            sSc2[b][t] = __dmul_rn(sc, sc);
+            sSc[b][t] = (KER == 1) ? __dmul_rn(-0.5, __dmul_rn(sc, sc)) : sc;
         }
         __syncthreads();
         if (gj >= a.nQ) continue;
-        for (int b = 0; b < nb; ++b) {
+        double* colp = a.M + (long)(g.first + b0) * a.strideM + colOffset;
+        for (int b = 0; b < nb; ++b, colp += a.strideM) {
             double S[4] = {0.0, 0.0, 0.0, 0.0}, Pr[4] = {1.0, 1.0, 1.0, 1.0};
+            double scv[FNT];
+#pragma unroll
+            for (int t = 0; t < FNT; t += 2) {
+                const double2 s2 = *reinterpret_cast<const double2*>(&sSc[b][t]);
+                scv[t] = s2.x; scv[t + 1] = s2.y;
+            }
 #pragma unroll
             for (int t = 0; t < FNT; ++t) {
                 if (t < nterms) {
-                    const double sc = sSc[b][t];
-                    if (KER == 1 && ((groupMask >> t) & 1u)) {
-                        const double sc2 = sSc2[b][t];
+                    const double sc = scv[t];
+                    if (KER == 1) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) S[i] = fma(q[i][t], sc2, S[i]);
+                        for (int i = 0; i < 4; ++i) S[i] = fma(q[i][t], sc, S[i]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const double av = __dmul_rn(q[i][t], sc);
-                            if (KER == 1) S[i] = fma(av, av, S[i]);
-                            else {
-                                S[i] = __dadd_rn(S[i], av);
-                                if (KER == 2) Pr[i] = __dmul_rn(Pr[i], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
-                                else Pr[i] = __dmul_rn(Pr[i], __dadd_rn(1.0, av));
-                            }
+                            S[i] = __dadd_rn(S[i], av);
+                            if (KER == 2) Pr[i] = __dmul_rn(Pr[i], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
+                            else Pr[i] = __dmul_rn(Pr[i], __dadd_rn(1.0, av));
                         }
                     }
                 }
             }
-            double v[4];
+            double raw[4], v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                double r = (KER == 1) ? exp_nonpos(__dmul_rn(-0.5, S[i]), sExp) : __dmul_rn(Pr[i], exp_nonpos(-S[i], sExp));
-                if (a.rowOff + gi0 + i == a.colOff + gj) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
-                else if (scaled) r = __dmul_rn(r, a.mult);
-                v[i] = r;
+                raw[i] = (KER == 1) ? exp_nonpos(S[i], sExp) : __dmul_rn(Pr[i], exp_nonpos(-S[i], sExp));
+                v[i] = scaled ? __dmul_rn(raw[i], a.mult) : raw[i];
             }
-            double* colp = a.M + (long)(g.first + b0 + b) * a.strideM + (long)(a.colOff + gj) * a.ld + a.rowOff;
+            if (dgi < 4u) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int gi = gi0 + 2 * h;
-                if (gi + 1 < a.nP && ((reinterpret_cast<uintptr_t>(colp + gi) & 15) == 0)) {
-                    *reinterpret_cast<double2*>(colp + gi) = make_double2(v[2 * h], v[2 * h + 1]);
-                } else {
-                    if (gi < a.nP) colp[gi] = v[2 * h];
-                    if (gi + 1 < a.nP) colp[gi + 1] = v[2 * h + 1];
-                }
+                for (int i = 0; i < 4; ++i)
+                    if ((unsigned)i == dgi) v[i] = fma(a.mult, __dadd_rn(raw[i], a.diag_rel), a.diag_abs);
+            }
+            if (full4) {
+                *reinterpret_cast<double2*>(colp) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2*>(colp + 2) = make_double2(v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (gi0 + i < a.nP) colp[i] = v[i];
             }
         }
     }
