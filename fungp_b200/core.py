@@ -56,6 +56,8 @@ class Context:
             raise FgpError(f"fgp_ctx_create failed ({rc}): no sm_100 CUDA device visible -- fungp_b200 has no CPU path")
         self.h = h
         self._problems = weakref.WeakSet()
+        # every L_out of this mirror comes from numpy.zeros (calloc): the library need not clear the upper triangle
+        self.set_option("out_prezeroed", 1)
 
     def close(self):
         if getattr(self, "h", None):

@@ -141,6 +141,10 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "la_r8")) ctx->la_r8 = std::max(0, (int)value);
     else if (!strcmp(name, "la_r4")) ctx->la_r4 = std::max(0, (int)value);
     else if (!strcmp(name, "pdl")) ctx->pdl = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "host_threads")) ctx->host_threads = std::max(0, std::min((int)value, 64));
+    else if (!strcmp(name, "out_prezeroed")) ctx->out_prezeroed = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "host_thp")) ctx->host_thp = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "gemm_flat")) ctx->gemm_flat = value < 0 ? 0 : (int)value;
     else if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value != 0 ? 1 : 0; g_plain_tma = ctx->gemm_tma; }
     else if (!strcmp(name, "fused_assembly")) ctx->fused_assembly = value != 0 ? 1 : 0;
     else if (!strcmp(name, "fit_points")) ctx->fit_points = std::max(0, std::min((int)value, 4096));

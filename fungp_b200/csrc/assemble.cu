@@ -111,12 +111,23 @@ __device__ __forceinline__ double exp_nonpos(double t, const double2* sTab) {
     return __hiloint2double(under ? 0 : hi, under ? 0 : __double2loint(res));
 }
 
+// One length-scale term of a Matern kernel, a = d * sc (sc = sqrt(3 or 5) / theta): the argument of the single exp
+// gathers -a, the polynomial factors multiply up.  matern3_2: 1 + a;  matern5_2: 1 + a + a^2 / 3 = 1 + d (sc + d c2),
+// c2 = sc^2 / 3.  Three / four FP64 operations per term; both assembly kernels call this, so they round alike.
+__device__ __forceinline__ double matern52_c2(double sc) { return __dmul_rn(__dmul_rn(sc, sc), 1.0 / 3.0); }
+template <int KER>
+__device__ __forceinline__ void matern_term(double d, double sc, double c2, double& S, double& Pr) {
+    S = fma(d, -sc, S);
+    if (KER == 2) Pr = __dmul_rn(Pr, fma(d, fma(d, c2, sc), 1.0));
+    else Pr = __dmul_rn(Pr, fma(d, sc, 1.0));
+}
+
 // KER: 0 = raw distance of the (single) term, 1 gauss, 2 matern5_2, 3 matern3_2
 template <int KER, int MODE>
 __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
     __shared__ __align__(16) double sP[CC][AT];
     __shared__ __align__(16) double sQ[CC][AT];
-    __shared__ double sScale[CC];
+    __shared__ double sScale[CC], sScale2[CC];
     __shared__ int sCol[CC];
     __shared__ int sFlag[CC];       // bit 0: member of a group term, bit 1: last unit of its term
     __shared__ double sRed[ATHREADS / 32];
@@ -164,6 +175,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
             const double sc = (KER == 0) ? 1.0 : scale[un.term];
             // gauss: -theta^-2 / 2 multiplies the SQUARED difference, so the sum arrives as the argument of the exp
             sScale[tid] = (KER == 1) ? __dmul_rn(-0.5, __dmul_rn(sc, sc)) : sc;
+            if (KER == 2) sScale2[tid] = matern52_c2(sc);
         }
         __syncthreads();
         // stage nc columns x 64 points of each side (coalesced along points)
@@ -184,6 +196,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
             const double xq[4] = {q01.x, q01.y, q23.x, q23.y};
             const int flag = sFlag[c];
             const double sc = sScale[c];
+            const double sc2 = (KER == 2) ? sScale2[c] : 0.0;
             if (!(flag & 1)) {
                 // index unit: scalar input or one L2_byindex coefficient, its own length-scale
 #pragma unroll
@@ -195,13 +208,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                         else {
                             // explicit roundings (no contraction left to the compiler): assemble_fused_kernel repeats these
                             // operations one for one and must give the same bits
-                            if (KER == 1) { S[i][j] = fma(__dmul_rn(d, d), sc, S[i][j]); continue; }
-                            const double av = __dmul_rn(d, sc);
-                            {
-                                S[i][j] = __dadd_rn(S[i][j], av);
-                                if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
-                                else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
-                            }
+                            if (KER == 1) S[i][j] = fma(__dmul_rn(d, d), sc, S[i][j]);
+                            else matern_term<KER>(d, sc, sc2, S[i][j], Pr[i][j]);
                         }
                     }
             } else {
@@ -222,12 +230,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
                             D2[i][j] = 0.0;
                             if (KER == 0) S[i][j] = sqrt(d2);
                             else if (KER == 1) S[i][j] = fma(d2, sc, S[i][j]);
-                            else {
-                                const double av = __dmul_rn(sqrt(d2), sc);
-                                S[i][j] = __dadd_rn(S[i][j], av);
-                                if (KER == 2) Pr[i][j] = __dmul_rn(Pr[i][j], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
-                                else Pr[i][j] = __dmul_rn(Pr[i][j], __dadd_rn(1.0, av));
-                            }
+                            else matern_term<KER>(sqrt(d2), sc, sc2, S[i][j], Pr[i][j]);
                         }
                 }
             }
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
             double r;
             if (KER == 0) r = S[i][j];
             else if (KER == 1) r = exp_nonpos(S[i][j], sExp);
-            else r = __dmul_rn(Pr[i][j], exp_nonpos(-S[i][j], sExp));
+            else r = __dmul_rn(Pr[i][j], exp_nonpos(S[i][j], sExp));
             if (KER != 0) {
                 if (diagTile && lr[i] == lc0 + j) r = fma(a.mult, __dadd_rn(r, a.diag_rel), a.diag_abs);
                 else if (scaled) r = __dmul_rn(r, a.mult);
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
     __shared__ __align__(16) double sP[FCC][FR];
     __shared__ __align__(16) double sQ[FCC][FC];
     __shared__ __align__(16) double sSc[FBCH][FNT];   // gauss: -scale^2 / 2 (multiplies squared differences); Matern: scale
+    __shared__ __align__(16) double sSc2[KER == 2 ? FBCH : 1][FNT];   // matern5_2: scale^2 / 3
     __shared__ int sCol[FCC], sFlag[FCC], sTermFirst[FNT + 1], sNterms;
     __shared__ double2 sExp[32];
     load_exp_table(sExp);
@@ -349,12 +353,14 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
         sFlag[tid] = (un.kind ? 1 : 0) | (un.last ? 2 : 0);
     }
     __syncthreads();
-    if (tid == 0) {
-        int t = 0;
-        sTermFirst[0] = 0;
-        for (int u = 0; u < nunits; ++u)
-            if (sFlag[u] & 2) sTermFirst[++t] = u + 1;
-        sNterms = t;
+    if (tid < 32) {
+        // first unit of every term: a term ends at a unit flagged `last`; prefix counts by ballot (nunits <= FCC <= 64)
+        const bool l0 = tid < nunits && (sFlag[tid] & 2), l1 = tid + 32 < nunits && (sFlag[tid + 32] & 2);
+        const unsigned m0 = __ballot_sync(0xffffffffu, l0), m1 = __ballot_sync(0xffffffffu, l1);
+        const unsigned below = (1u << tid) - 1u;
+        if (l0) sTermFirst[__popc(m0 & below) + 1] = tid + 1;
+        if (l1) sTermFirst[__popc(m0) + __popc(m1 & below) + 1] = tid + 33;
+        if (tid == 0) { sTermFirst[0] = 0; sNterms = __popc(m0) + __popc(m1); }
     }
     for (int idx = tid; idx < nunits * FR; idx += FTHREADS) {
         const int c = idx / FR, pnt = idx % FR;
@@ -418,6 +424,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
                 sc = scale[t];
             }
             sSc[b][t] = (KER == 1) ? __dmul_rn(-0.5, __dmul_rn(sc, sc)) : sc;
+            if (KER == 2) sSc2[b][t] = matern52_c2(sc);
         }
         __syncthreads();
         if (gj >= a.nQ) continue;
@@ -438,20 +445,16 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) S[i] = fma(q[i][t], sc, S[i]);
                     } else {
+                        const double c2 = (KER == 2) ? sSc2[KER == 2 ? b : 0][t] : 0.0;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const double av = __dmul_rn(q[i][t], sc);
-                            S[i] = __dadd_rn(S[i], av);
-                            if (KER == 2) Pr[i] = __dmul_rn(Pr[i], fma(av, fma(av, 1.0 / 3.0, 1.0), 1.0));
-                            else Pr[i] = __dmul_rn(Pr[i], __dadd_rn(1.0, av));
-                        }
+                        for (int i = 0; i < 4; ++i) matern_term<KER>(q[i][t], sc, c2, S[i], Pr[i]);
                     }
                 }
             }
             double raw[4], v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                raw[i] = (KER == 1) ? exp_nonpos(S[i], sExp) : __dmul_rn(Pr[i], exp_nonpos(-S[i], sExp));
+                raw[i] = (KER == 1) ? exp_nonpos(S[i], sExp) : __dmul_rn(Pr[i], exp_nonpos(S[i], sExp));
                 v[i] = scaled ? __dmul_rn(raw[i], a.mult) : raw[i];
             }
             if (dgi < 4u) {

@@ -72,6 +72,7 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
     base.maxTilesPerCta = la_pre ? 1 : 0;
     base.pdl = pdlMode;
     base.tma = ctx->gemm_tma;
+    base.flat = ctx->gemm_flat;
 
     cudaEvent_t evPanel = nullptr, evBulk = nullptr;
     const bool la = lookahead && sBulk != nullptr && sBulk != sPanel && t.batch == 1 && !ctx->profile;

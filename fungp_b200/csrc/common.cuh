@@ -130,6 +130,8 @@ struct GemmArgs {
     int maxTilesPerCta;                        // 0 = automatic; 1 = one tile per CTA (look-ahead: the panel stream must find a free SM quickly)
     int dbg;                                   // experiment switches, honoured only when built with -DFGP_GEMM_DEBUG
     int tma;                                   // 1: operands by TMA (gemm_tma.cu), 0: per-thread cp.async (gemm_dmma.cu)
+    int flat;                                  // TMA kernel: > 0 = walk all (tile, element) pairs with one CTA per SM when there are at least
+                                               // flat x SMs of them and K <= 1024 (batches of small matrices); 0 = never
     int pdl;                                   // 1: programmatic dependent launch (the prologue overlaps the previous kernel's tail); 2: also
                                                // release the dependents at once (single-factorisation chain: the next kernel waits resident)
 };

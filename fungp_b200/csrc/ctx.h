@@ -110,6 +110,10 @@ struct fgp_ctx {
     int fit_workers = 8;      // fgp_fit_batch, fit_mode 0: concurrent candidate fits (host threads) per GPU
     int fit_mode = 1;         // 1: lock-step -- one host thread per GPU advances all in-flight candidates together (fitlock.cu); 0: one thread per candidate
     int gemm_tma = 1;         // operands of the DMMA GEMM by TMA (gemm_tma.cu); 0 = cp.async kernel
+    int host_threads = 0;     // host threads of the chunked matrix transfers; 0 = min(16, cores)
+    int out_prezeroed = 0;    // 1: the caller's L_out matrices are zero-filled on entry (calloc / numpy.zeros): only the lower triangle is written
+    int host_thp = 1;         // ask for transparent huge pages on large host output matrices (model.cu copy_matrix)
+    int gemm_flat = 8;        // TMA kernel: persistent CTAs over all (tile, element) pairs from this many pairs per SM on (0 = never)
     int pdl = 1;              // programmatic dependent launch along the factorisation's kernel chain
     int fused_assembly = 1;   // batched likelihood calls assemble the matrices of one structure with the batch-fused kernel
     int fit_points = 0;       // lock-step: likelihood points per round and lane (0 = by memory, at most 512)

@@ -731,7 +731,7 @@ int fit_lockstep(fgp_ctx* ctx, Shared& S, const std::vector<int>& order) {
             cudaSetDevice(device);
             wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
             wc->fit_points = ctx->fit_points; wc->fit_lanes = ctx->fit_lanes; wc->predict_reserve = ctx->predict_reserve;
-            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma;
+            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat;
             wc->blockingSync = ctx->fit_blocking > 0 ? ctx->fit_blocking : 0;
             // option "profile": per-launch CUDA events of this call's rounds on the first GPU (meaningful with fit_lanes = 1,
             // where the rounds do not overlap); fgp_get_timing on the caller's context reports them

@@ -114,12 +114,11 @@ __device__ __forceinline__ TileId decode_tile(const GemmArgs& g, int t) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int flat, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const long b = blockIdx.y;
     const int nchunks = (g.K + KC - 1) / KC;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t fullB = sbase + SMEM_BYTES;            // full[s]  at +8 s
@@ -136,17 +135,20 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap
     // programmatic dependent launch: everything above overlapped the previous kernel's tail
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     if (g.pdl == 2) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    // (Tried: one 1-D grid over all (tile, batch element) pairs, so that the ring also runs through matrix boundaries of
-    // small-n batches.  Measured 4 % slower at n = 1024 x 60 -- tiles differ in cost (one-row y tiles, diagonal tiles) and
-    // many short CTAs balance better than few long ones -- and no different at n = 8192; one grid row per batch element stays.)
+    // Work items are (tile, batch element) pairs.  Default: one grid row per batch element, a CTA walks the tiles
+    // blockIdx.x, blockIdx.x + gridDim.x, ... of its element.  flat: a 1-D grid of one CTA per SM walks ALL pairs,
+    // element-major, so the operand ring also runs through matrix boundaries -- for small-n batches with hundreds of
+    // elements (lock-step candidate scoring) every CTA would otherwise do a single short tile and pay the ring's fill
+    // and drain each time.  With few items per CTA the static deal balances worse than many short CTAs (one-row y
+    // tiles and diagonal tiles are cheaper: -4 % at n = 1024 x 60), so the launcher turns it on only for long queues.
+    const int nitems = flat ? ntiles * g.batch : ntiles;
     int tIdx = blockIdx.x;
-    if (tIdx >= ntiles) return;
+    if (tIdx >= nitems) return;
     const Valid rv{g.rowMin, g.rowLo, g.rowHoleHi, g.nrows};
     const Valid cv{g.colMin, g.colLo, g.colHoleHi, g.ncols};
     // warps (wm, wn): 4 along m (32 rows each) x 2 along n (64 cols each); same assignment as gemm_dmma_kernel
     const int wn = (warp >> 2) & 1;
     const int wm = (warp + wn) & 3;
-    double* C = g.C + b * g.strideC;
     const int sgnmask = g.accumulate ? (int)0x80000000 : 0;   // C -= A B': flip the sign bit of the A fragments (integer op)
     const int r_lane = lane >> 2;        // row within an 8x8 DMMA tile
     const int c_lane = 2 * (lane & 3);   // first of the two columns this lane owns
@@ -159,19 +161,22 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap
         for (int s = 0; s < STAGES - 1; ++s) {
             const int off = s / nchunks, cn = s - off * nchunks;
             const int tgt = tIdx + off * (int)gridDim.x;
-            if (tgt < ntiles) {
-                const TileId t1 = decode_tile(g, tgt);
+            if (tgt < nitems) {
+                const int b1 = flat ? tgt / ntiles : (int)blockIdx.y;
+                const TileId t1 = decode_tile(g, tgt - (flat ? b1 * ntiles : 0));
                 mbar_expect_tx(fullB + 8 * s, STAGE_TX);
                 const uint32_t dst = sbase + (uint32_t)(s * STAGE * 8);
-                tma_load_3d(dst, &mapA, fullB + 8 * s, t1.I * FGP_TILE, cn * KC, (int)b);
-                tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * s, (t1.J - g.bTileBase) * FGP_TILE, cn * KC, (int)b);
+                tma_load_3d(dst, &mapA, fullB + 8 * s, t1.I * FGP_TILE, cn * KC, b1);
+                tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * s, (t1.J - g.bTileBase) * FGP_TILE, cn * KC, b1);
             }
         }
     }
 
     int gc = 0;   // global chunk counter of this CTA (ring position)
-    for (; tIdx < ntiles; tIdx += gridDim.x) {
-        const TileId tl = decode_tile(g, tIdx);
+    for (; tIdx < nitems; tIdx += gridDim.x) {
+        const int b = flat ? tIdx / ntiles : (int)blockIdx.y;
+        const TileId tl = decode_tile(g, tIdx - (flat ? b * ntiles : 0));
+        double* C = g.C + (long)b * g.strideC;
         const int rowBase = tl.I * FGP_TILE;
         const int colBase = (tl.J - g.bTileBase) * FGP_TILE;
         const int wrow = rowBase + wm * 32;
@@ -235,11 +240,13 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap
             const int off = ahead / nchunks;
             const int cn = ahead - off * nchunks;
             const int tgt = tIdx + off * (int)gridDim.x;
-            const bool doCopy = tgt < ntiles;
+            const bool doCopy = tgt < nitems;
+            const int bn = (flat && doCopy) ? tgt / ntiles : b;               // batch element / tile of that chunk
+            const int tn = tgt - (flat ? bn * ntiles : 0);
             if (off > 0 && doCopy && cn == 0 && g.accumulate) {
                 // pull that tile's C into L2: 128 columns x 8 lines of 128 bytes, 4 lines per thread
-                const TileId t1 = decode_tile(g, tgt);
-                const double* Cn = C + (long)t1.I * FGP_TILE + (long)((t1.J - g.bTileBase) * FGP_TILE) * g.ldc;
+                const TileId t1 = decode_tile(g, tn);
+                const double* Cn = g.C + (long)bn * g.strideC + (long)t1.I * FGP_TILE + (long)((t1.J - g.bTileBase) * FGP_TILE) * g.ldc;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int q = tid + THREADS * i;
@@ -262,13 +269,13 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, const __grid_constant__ CUtensorMap
                     if (gc + STAGES - 1 >= STAGES) mbar_wait(emptyB + 8 * sn, (((gc + STAGES - 1) / STAGES) - 1) & 1);
                     int rb = rowBase, cb = colBase;
                     if (off > 0) {
-                        const TileId t1 = decode_tile(g, tgt);
+                        const TileId t1 = decode_tile(g, tn);
                         rb = t1.I * FGP_TILE; cb = (t1.J - g.bTileBase) * FGP_TILE;
                     }
                     mbar_expect_tx(fullB + 8 * sn, STAGE_TX);
                     const uint32_t dst = sbase + (uint32_t)(sn * STAGE * 8);
-                    tma_load_3d(dst, &mapA, fullB + 8 * sn, rb, cn * KC, (int)b);
-                    tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * sn, cb, cn * KC, (int)b);
+                    tma_load_3d(dst, &mapA, fullB + 8 * sn, rb, cn * KC, bn);
+                    tma_load_3d(dst + OPER * 8, &mapB, fullB + 8 * sn, cb, cn * KC, bn);
                 }
                 if (mult) {
                     double a[4], bb[8];
@@ -379,14 +386,20 @@ bool launch_gemm_tma(const GemmArgs& g, cudaStream_t st) {
         const int want = (ntiles + tpc - 1) / tpc;
         gx = want <= sms ? std::min(ntiles, sms) : std::min(ntiles, ((want + sms - 1) / sms) * sms);
     }
+    // long queues of short tiles: one persistent CTA per SM over all (tile, element) pairs (see the kernel)
+    int flat = 0;
+    if (g.flat > 0 && g.batch > 1 && g.maxTilesPerCta != 1 && g.K <= 1024 && (long)ntiles * g.batch >= (long)g.flat * sms) {
+        flat = 1;
+        gx = sms;
+    }
     FGP_COUNT_LAUNCH();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(gx, g.batch); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES + 64; cfg.stream = st;
+    cfg.gridDim = dim3(gx, flat ? 1 : g.batch); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES + 64; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g.pdl ? 1 : 0;
     GemmArgs gg = g;
-    if (gg.pdl == 2 && (long)gx * g.batch > sms) gg.pdl = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_dmma_tma_kernel, gg, ntiles, mapA, mapB) == cudaSuccess;
+    if (gg.pdl == 2 && (long)gx * (flat ? 1 : g.batch) > sms) gg.pdl = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_dmma_tma_kernel, gg, ntiles, flat, mapA, mapB) == cudaSuccess;
 }

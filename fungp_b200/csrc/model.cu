@@ -7,6 +7,7 @@
 // them against the resident factor IN PLACE (the trapezoid engine of chol.cu with every column tile prefactored), so
 // no copy of L is made per call.  More new points than reserved rows are processed in chunks (predictions of different
 // points are independent); only a simulate call with more points than rows falls back to a private copy.
+#include <sys/mman.h>
 #include "ctx.h"
 #include "../../include/fungp_b200.h"
 #include <cstring>
@@ -51,9 +52,11 @@ int ensure_stage(fgp_ctx* ctx, DevState& d) {
 
 // run fn(t, nthreads) on a few host threads
 template <class F>
-void host_parallel(long work_bytes, F fn) {
+void host_parallel(int want, long work_bytes, F fn) {
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::max(1u, std::min(8u, hw / 2));
+    // writing a fresh destination is bound by page faults per thread: 4 / 8 / 12 / 16 threads move the factor of n = 32768
+    // at 11 / 14-17 / 20 / 23 GB/s (tools/lout_probe.py), so all cores up to 16 take part for the length of the copy
+    int nt = want > 0 ? want : (int)std::max(1u, std::min(16u, hw));
     if (work_bytes < (4 << 20)) nt = 1;
     if (nt == 1) { fn(0, 1); return; }
     std::vector<std::thread> th;
@@ -81,13 +84,13 @@ int copy_matrix(fgp_ctx* ctx, DevState& d, bool toHost, double* host, long ldh, 
         c0 += w;
     }
     auto host_side = [&](const Chunk& ch, double* buf) {       // staging <-> caller's matrix
-        host_parallel(ch.rows * (ch.c1 - ch.c0) * 8, [&](int t, int nt) {
+        host_parallel(ctx->host_threads, ch.rows * (ch.c1 - ch.c0) * 8, [&](int t, int nt) {
             for (long c = ch.c0 + t; c < ch.c1; c += nt) {
                 double* hcol = host + c * ldh;
                 double* scol = buf + (c - ch.c0) * ch.rows;
                 const long skip = lower ? c - ch.r0 : 0;       // rows of this column above the diagonal inside the chunk
                 if (toHost) {
-                    if (lower) memset(hcol, 0, sizeof(double) * (size_t)std::min(c, rows));
+                    if (lower && !ctx->out_prezeroed) memset(hcol, 0, sizeof(double) * (size_t)std::min(c, rows));
                     memcpy(hcol + ch.r0 + skip, scol + skip, sizeof(double) * (size_t)(ch.rows - skip));
                 } else {
                     if (skip) memset(scol, 0, sizeof(double) * (size_t)skip);
@@ -106,6 +109,14 @@ int copy_matrix(fgp_ctx* ctx, DevState& d, bool toHost, double* host, long ldh, 
     };
     const int nc = (int)chunks.size();
     cudaError_t e = cudaSuccess;
+    if (toHost && ctx->host_thp && (size_t)cols * ldh * sizeof(double) >= ((size_t)64 << 20)) {
+        // The caller's matrix is usually fresh memory (R's allocVector, numpy.empty): writing it is bound by page faults
+        // -- 2.1 M of them for the 8.6 GB factor of n = 32768.  Ask for transparent huge pages on the 2 MB-aligned
+        // interior; a hint only, ignored where THP is off, harmless on memory that is already populated.
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(host) + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(host) + (size_t)cols * ldh * sizeof(double)) & ~(uintptr_t)((2u << 20) - 1);
+        if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+    }
     if (toHost) {
         for (int i = 0; i < nc + 1 && e == cudaSuccess; ++i) {
             if (i < nc) { e = bus(chunks[i], stage[i & 1]); if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st); }
@@ -114,7 +125,7 @@ int copy_matrix(fgp_ctx* ctx, DevState& d, bool toHost, double* host, long ldh, 
                 if (e == cudaSuccess) host_side(chunks[i - 1], stage[(i - 1) & 1]);
             }
         }
-        if (lower && e == cudaSuccess)                         // columns that had no rows at all (cols > rows)
+        if (lower && !ctx->out_prezeroed && e == cudaSuccess)  // columns that had no rows at all (cols > rows)
             for (long c = rows; c < cols; ++c) memset(host + c * ldh, 0, sizeof(double) * (size_t)rows);
     } else {
         for (int i = 0; i < nc && e == cudaSuccess; ++i) {

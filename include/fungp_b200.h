@@ -201,7 +201,14 @@ int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
  * "fit_mode", "fit_points", "fit_lanes" (see fgp_fit_batch), "predict_reserve" (rows kept free under a stored factor),
  * "blocking_sync" (0/1/2, default 0: the same for this context's own calls),
  * "graphs" (0/1, default 0: batched likelihood calls at n < 2048 are captured as a CUDA graph the second time a shape is
- * seen on a problem and replayed afterwards -- one driver call per evaluation batch instead of ~30). */
+ * seen on a problem and replayed afterwards -- one driver call per evaluation batch instead of ~30),
+ * "fused_assembly", "pdl", "gemm_tma" (0/1, default 1: the batch-fused assembly kernel, programmatic dependent launch,
+ * TMA operand path of the DMMA GEMM), "gemm_flat" (default 8: batched GEMM launches with at least this many tiles per SM
+ * and K <= 1024 run one persistent CTA per SM over all (tile, matrix) pairs; 0 = never), "la_r8", "la_r4" (look-ahead
+ * panel width thresholds in remaining tile columns), "host_threads" (host threads of the chunked L / K.tp transfers,
+ * default 0 = min(16, cores)), "host_thp" (0/1, default 1: MADV_HUGEPAGE hint on host outputs of 64 MB and more),
+ * "out_prezeroed" (0/1, default 0: the caller guarantees that every L_out it passes is zero-filled on entry, e.g. from
+ * calloc; the library then writes the lower triangle only instead of also clearing the upper one). */
 int fgp_set_option(fgp_ctx* ctx, const char* name, double value);
 /* measured FP64 peaks on device 0 for the roofline denominators: register-resident DMMA (m8n8k4) loop and
  * DFMA loop, TFLOP/s; and a device copy, GB/s. */

@@ -282,3 +282,36 @@ def test_lockstep_optimizer_option_matches_host_optimizer(ctx):
     assert np.max(np.abs(gl.preMats["L"] - o2.L)) <= 1e-9 * np.max(np.abs(o2.L))
     assert abs(M.loocv_q2(gl) - ref.q2_loocv(o2)) <= 1e-8
     gh.close(); gl.close()
+
+
+def test_L_out_upper_triangle_contract(ctx):
+    """preMats$L has explicit zeros above the diagonal (R/3_training_SF.R:262: t(chol(.))).  By default the library clears
+    the upper triangle of whatever buffer it is handed (R's allocMatrix is not zero-filled); with the option
+    "out_prezeroed" the caller vouches for a zero-filled buffer and only the lower triangle is written.  Raw C-ABI calls,
+    buffers pre-filled with NaN; sizes on both sides of the chunking (one 48 MB stage holds n <= ~2500 columns)."""
+    import ctypes as C
+    import fungp_b200
+    from fungp_b200.core import KER, _dp
+    for n in (333, 2900):
+        sIn, fIn, y, _ = synth_problem(17, n, 2, [25])
+        proj = [ctx.project(f, 3, "B-splines") for f in fIn]
+        P = fungp_b200.Problem(ctx, sIn, [c for (_, _, c) in proj], [j for (_, j, _) in proj], ["L2_bygroup"], y)
+        theta = 0.4 * 2.0 * P.dist_max()
+        _, s2, _ = P.nll_batch("matern5_2", 1e-8, theta)
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        out = {}
+        try:
+            for pz in (0, 1):
+                ctx.set_option("out_prezeroed", pz)
+                L = np.full((n, n), np.nan, order="F"); z = np.zeros(n)
+                rc = ctx.lib.fgp_premats(P.h, KER["matern5_2"], 1e-8, float(s2[0]), _dp(th), _dp(L), _dp(z))
+                assert rc == 0
+                out[pz] = L
+        finally:
+            ctx.set_option("out_prezeroed", 1)        # the mirror's own setting (numpy.zeros buffers)
+        iu = np.triu_indices(n, 1)
+        assert np.all(out[0][iu] == 0.0)                               # cleared by the library
+        assert np.all(np.isnan(out[1][iu]))                            # left alone: the caller said it is zero already
+        il = np.tril_indices(n)
+        assert np.all(np.isfinite(out[0][il])) and np.array_equal(out[0][il], out[1][il])
+        P.close()
