@@ -84,9 +84,17 @@ __device__ const double2 g_exp_tab[32] = {
     {1.91520656139714740e+00, -1.06199460561959626e-16},
     {1.95714412417540018e+00, 8.96076779103666777e-17}};
 
+// The table sits in shared memory eight times over, entry e of copy c at 16-byte slot 8 e + c: a lane only ever reads
+// copy (lane & 7), so the eight lanes of a quarter-warp (the unit a 16-byte shared load is served in) hit eight
+// different bank groups whatever their arguments are.  With a single copy the data-dependent indices of neighbouring
+// entries collided: ncu counted 96 M bank-conflict cycles per 436 M lookups, ~7 extra wavefronts per warp load.
+constexpr int EXP_COPIES = 8;
+constexpr int EXP_TAB_SLOTS = 32 * EXP_COPIES;
 __device__ __forceinline__ void load_exp_table(double2* sTab) {
-    if (threadIdx.x < 32) sTab[threadIdx.x] = g_exp_tab[threadIdx.x];
+    if (threadIdx.x < EXP_TAB_SLOTS) sTab[threadIdx.x] = g_exp_tab[threadIdx.x / EXP_COPIES];
 }
+// this lane's copy: pass the result to exp_nonpos
+__device__ __forceinline__ const double2* exp_table_of_lane(const double2* sTab) { return sTab + (threadIdx.x & (EXP_COPIES - 1)); }
 
 __device__ __forceinline__ double exp_nonpos(double t, const double2* sTab) {
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: rounds to nearest integer in the low word
@@ -101,7 +109,7 @@ __device__ __forceinline__ double exp_nonpos(double t, const double2* sTab) {
     p = fma(p, r, 1.66666666666666666667e-01);             // 1/3!
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
-    const double2 T = sTab[k & 31];
+    const double2 T = sTab[(k & 31) * EXP_COPIES];
     double res = fma(T.x, __dmul_rn(r, p), T.x);           // T_hi (1 + r p)
     res = __dadd_rn(res, T.y);
     // below about -708.0002 the result would leave the normal range (the exponent is patched by integer addition): flush to
@@ -131,8 +139,9 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_kernel(AsmK k) {
     __shared__ int sCol[CC];
     __shared__ int sFlag[CC];       // bit 0: member of a group term, bit 1: last unit of its term
     __shared__ double sRed[ATHREADS / 32];
-    __shared__ double2 sExp[32];
-    if (KER != 0) load_exp_table(sExp);      // visible after the barriers of the staging loop below
+    __shared__ double2 sExpAll[EXP_TAB_SLOTS];
+    if (KER != 0) load_exp_table(sExpAll);   // visible after the barriers of the staging loop below
+    const double2* sExp = exp_table_of_lane(sExpAll);
     const AsmArgs& a = k.a;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -328,8 +337,9 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
     __shared__ __align__(16) double sSc[FBCH][FNT];   // gauss: -scale^2 / 2 (multiplies squared differences); Matern: scale
     __shared__ __align__(16) double sSc2[KER == 2 ? FBCH : 1][FNT];   // matern5_2: scale^2 / 3
     __shared__ int sCol[FCC], sFlag[FCC], sTermFirst[FNT + 1], sNterms;
-    __shared__ double2 sExp[32];
-    load_exp_table(sExp);
+    __shared__ double2 sExpAll[EXP_TAB_SLOTS];
+    load_exp_table(sExpAll);
+    const double2* sExp = exp_table_of_lane(sExpAll);
     const AsmArgs& a = k.a;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;             // rows 4tx..4tx+3, column ty
