@@ -120,7 +120,7 @@ extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
         if (d.evA) cudaEventDestroy(d.evA);
         if (d.evB) cudaEventDestroy(d.evB);
         if (d.evWait) cudaEventDestroy(d.evWait);
-        d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release(); d.pool.release();
+        d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release(); d.dagFlags.release(); d.pool.release();
         if (d.pinned) cudaFreeHost(d.pinned);
     }
     delete ctx;
@@ -144,6 +144,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "host_threads")) ctx->host_threads = std::max(0, std::min((int)value, 64));
     else if (!strcmp(name, "out_prezeroed")) ctx->out_prezeroed = value != 0 ? 1 : 0;
     else if (!strcmp(name, "host_thp")) ctx->host_thp = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "dag")) ctx->dag = value != 0 ? 1 : 0;
     else if (!strcmp(name, "gemm_flat")) ctx->gemm_flat = value < 0 ? 0 : (int)value;
     else if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value != 0 ? 1 : 0; g_plain_tma = ctx->gemm_tma; }
     else if (!strcmp(name, "fused_assembly")) ctx->fused_assembly = value != 0 ? 1 : 0;
@@ -550,6 +551,9 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
         int ns = prof ? 1 : std::min(ctx->streams, cb);
         if (n < 2048) ns = 1;
         else if (n < 4096) ns = std::min(ns, 2);
+        // dataflow Cholesky: the whole chunk in one persistent launch (one group, one stream)
+        const bool useDag = ctx->dag && !prof && chol_dag_supported(n, n + 1) && !d.dagFlags.ensure(chol_dag_flag_bytes(n, cb));
+        if (useDag) ns = 1;
         const int per = cdiv(cb, ns);
         // The points of a batch share every coordinate difference: with enough of them ONE batch-fused assembly launch
         // builds all matrices of the chunk (bit-identical entries) on the first stream, and the groups fork from there;
@@ -598,8 +602,10 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             t.info = dInfo + g0;
             if (prof) d.timers.begin(st);
             cudaEvent_t fa = prof ? d.timers.cur : nullptr;
-            const int rcf = trap_factor(ctx, slot, t, st, d.sBulk, ctx->lookahead && ns == 1 && gb == 1);
-            if (rcf) return rcf;
+            if (!(useDag && launch_chol_dag(t.M, t.ld, t.strideM, gb, n, t.W, t.strideW, t.info, d.dagFlags.p, st))) {
+                const int rcf = trap_factor(ctx, slot, t, st, d.sBulk, ctx->lookahead && ns == 1 && gb == 1);
+                if (rcf) return rcf;
+            }
             if (prof) { d.timers.cur = fa; d.timers.end(st, FgpTimers::FACTOR, 0.0); }
             launch_nll_reduce(Mg, ld, (long)ld * n, gb, n, n, var_known ? dVar : nullptr, dInfo + g0, dNll + g0, dSig + g0, st);
             return 0;

@@ -1,0 +1,455 @@
+// The whole blocked Cholesky of a batch of (n + 1)-row trapezoids as ONE persistent dataflow kernel.
+//
+// Replaces, for the likelihood path (base::chol + backsolve of R/3_training_SF.R:249,267), the launch sequence of
+// chol.cu -- per column tile: diagonal-block kernel, panel-solve GEMM, one or more trailing-update GEMMs -- by a single
+// launch of one CTA per SM.  The unit of work is one 128x128 tile (i, j) of one matrix, done left-looking by ONE CTA
+// from start to finish:
+//     acc  = A(i,j)                                      the assembled tile, read once
+//     acc -= L(i, 0:j) L(j, 0:j)'                        K = 128 j through the TMA ring of gemm_tma.cu; a k-tile kt is
+//                                                        requested as soon as L(i,kt) and L(j,kt) are flagged ready
+//     i == j :  L(j,j), W_j = potf2(acc)                 potf2_body.cuh on the tile handed over in shared memory
+//     i >  j :  L(i,j) = acc W_j'                        once W_j is flagged; DMMA from shared memory
+//     store, __threadfence, flag (i,j) / W_j ready
+// Tiles are claimed from one atomic counter in an order in which every tile's inputs have smaller numbers -- column by
+// column, inside a column the diagonal tiles of all matrices first, then row by row over the matrices -- so a CTA only
+// ever waits for tiles that are already running or done on other resident CTAs: no deadlock whatever the number of
+// resident CTAs.  Why: (1) the chain diagonal block -> solve -> next diagonal block is walked at flag latency (~1-2 us)
+// instead of three kernel launches per column, and the CTAs holding later tiles fill in behind it; (2) every C tile is
+// read and written once instead of once per panel level; (3) batches of small matrices need one launch per round.
+// Numerics: per entry the same DMMA sequence in the same k order as the launch-per-step engine (whose updates also
+// accumulate k ascending, merely interrupted by exact stores and loads), the same potf2 code, the same zero-skipping in
+// the solve: results are bit-identical (tests/test_gpu_parity.py::test_dataflow_cholesky_is_bit_identical).
+// Scope: n a multiple of 128 (the y row then sits alone in row tile n / 128), no holes, nothing prefactored;
+// everything else stays on chol.cu.
+#include "potf2_body.cuh"
+#include <cuda.h>
+#include <algorithm>
+
+namespace {
+
+constexpr int KC = 32;
+constexpr int STAGES = 3;
+constexpr int PITCH = 132;
+constexpr int OPER = PITCH * KC;
+constexpr int STAGE = 2 * OPER;
+constexpr int RING_BYTES = STAGES * STAGE * 8;          // 202752; the first two stages double as the 128 x 132 hand-over tile
+constexpr int THREADS = 256;
+constexpr int MMA_WARPS = 8;
+constexpr uint32_t STAGE_TX = 2u * OPER * 8u;
+constexpr uint32_t SLAB_TX = OPER * 8u;
+constexpr int BAR_OFF = RING_BYTES;                     // full[3] | empty[3]
+constexpr int WBAR_OFF = BAR_OFF + 64;                  // wfull[2]: the two W slabs of the solve
+constexpr int PBAR_OFF = WBAR_OFF + 16;                 // potf2's 32 column barriers
+constexpr int TASK_OFF = PBAR_OFF + 8 * potf2::SB;
+constexpr int DAG_SMEM = TASK_OFF + 16;
+static_assert(potf2::POTF2_WORK_DOUBLES * 8 <= RING_BYTES, "potf2 works inside the ring's memory");
+static_assert(potf2::NB * potf2::LDT * 8 == 2 * STAGE * 8, "hand-over tile = stages 0 and 1");
+static_assert(potf2::LDT == PITCH, "one layout for the hand-over tile, potf2's T and the solve's A operand");
+
+struct DagArgs {
+    double* M; long ld; long strideM;
+    int batch, T, R, nrows;        // T column tiles, R = T + 1 row tiles, nrows = 128 T + 1
+    double* W; long strideW;
+    int* info;
+    int* flagL;                    // [batch][R][T]  L(i,j) stored
+    int* flagW;                    // [batch][T]     W_j (and L(j,j)) stored
+    int* counter;
+    int ntasks;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mbar_init(uint32_t addr, int count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(addr), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared.b64 st, [%0], %1;\n}\n" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, int parity) {
+    int ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n selp.b32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// Waits in this kernel can legitimately last as long as the factorisation (a CTA holding a late tile waits for the
+// chain), so the bound is a time, not a count: ~20 s of SM clock, then trap -- a protocol bug must never hang the device.
+constexpr long long SPIN_LIMIT_CLOCKS = 40000000000LL;
+__device__ __forceinline__ void mbar_wait(uint32_t addr, int parity) {
+    if (mbar_try_wait(addr, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(addr, parity))
+        if (clock64() - t0 > SPIN_LIMIT_CLOCKS) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int row, int k, int b) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(row), "r"(k), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// tile data were written with ordinary stores by another SM and are read here by the TMA unit (async proxy)
+__device__ __forceinline__ void wait_flag(const int* p) {
+    if (ld_acquire(p) == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire(p) == 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > SPIN_LIMIT_CLOCKS) __trap();
+        }
+    }
+    asm volatile("fence.proxy.async;\n" ::: "memory");
+}
+
+// the diagonal tile, handed over in shared memory: factor, store L(j,j) and W_j.  Not inlined: the block algorithm runs at
+// 255 registers on its own and must not share an allocation with the 128 accumulator registers of the tile loop.
+__device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* infoPtr, int infoOff, double* Mdiag, long ld, double* Wb) {
+    potf2::factor_block(smem, pbar, infoPtr, infoOff);
+    potf2::store_block(smem, Mdiag, ld, FGP_TILE, Wb);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __grid_constant__ CUtensorMap mapW) {
+    extern __shared__ __align__(128) double smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t fullB = sbase + BAR_OFF;
+    const uint32_t emptyB = fullB + 8 * STAGES;
+    const uint32_t wfullB = sbase + WBAR_OFF;
+    const uint32_t pbar = sbase + PBAR_OFF;
+    volatile int* sTask = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(smem) + TASK_OFF);
+    const bool producer = tid == 0;
+    if (producer) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, MMA_WARPS); }
+        mbar_init(wfullB, 1); mbar_init(wfullB + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapM)) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+    }
+    potf2::init_barriers(pbar);
+    __syncthreads();
+
+    // warps (wm, wn): 4 along m (32 rows each) x 2 along n (64 cols each), as in gemm_tma.cu
+    const int wn = (warp >> 2) & 1;
+    const int wm = (warp + wn) & 3;
+    const int r_lane = lane >> 2;
+    const int c_lane = 2 * (lane & 3);
+    const int aoff = (lane & 3) * PITCH + wm * 32 + r_lane;
+    const int boff = (lane & 3) * PITCH + wn * 64 + r_lane;
+    const int B = g.batch, R = g.R;
+
+    int gc = 0;   // chunks this CTA has sent through the ring so far (ring position and barrier phases)
+    for (;;) {
+        if (producer) *sTask = atomicAdd(g.counter, 1);
+        __syncthreads();
+        const int task = *sTask;
+        if (task >= g.ntasks) break;
+        // column j holds B (R - j) tasks; tasks before column j: B (j R - j (j - 1) / 2)
+        const int q = task / B;
+        int j = (int)(((float)(2 * R + 1) - sqrtf((float)(2 * R + 1) * (float)(2 * R + 1) - 8.0f * (float)q)) * 0.5f);
+        j = max(0, min(j, g.T - 1));
+        while (j + 1 < g.T && (j + 1) * R - (j + 1) * j / 2 <= q) ++j;
+        while (j > 0 && j * R - j * (j - 1) / 2 > q) --j;
+        const int local = task - B * (j * R - j * (j - 1) / 2);
+        const int i = j + local / B;
+        const int b = local - (local / B) * B;
+        const bool diag = i == j;
+        const int rowBase = i * FGP_TILE, colBase = j * FGP_TILE;
+        double* C = g.M + (long)b * g.strideM;
+        const int* fLi = g.flagL + ((long)b * R + i) * g.T;
+        const int* fLj = g.flagL + ((long)b * R + j) * g.T;
+        const int nchunks = j * (FGP_TILE / KC);
+        // Are all inputs of this tile there already?  (The usual case away from the start and the end of the
+        // factorisation.)  Then the producer never polls; otherwise it waits k-tile by k-tile as they are flagged.
+        bool ready = true;
+        for (int kt = tid; kt < j; kt += THREADS) {
+            ready = ready && ld_acquire(fLi + kt) != 0;
+            if (!diag) ready = ready && ld_acquire(fLj + kt) != 0;
+        }
+        const bool allReady = __syncthreads_and(ready) != 0;      // also: everybody has read the task slot
+
+        const int wrow = rowBase + wm * 32;
+        const int wcol = colBase + wn * 64;
+        unsigned rmask = 0;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+            if (wrow + mi * 8 + r_lane < g.nrows) rmask |= 1u << mi;
+        bool active = __any_sync(0xffffffffu, rmask != 0);
+        if (diag && (wm * 32 + 31 < wn * 64)) active = false;        // warps entirely above the diagonal
+        if (!active) rmask = 0;
+        const bool full = __all_sync(0xffffffffu, rmask == 0xFu);
+        unsigned mval = 0;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+            if (__any_sync(0xffffffffu, (rmask >> mi) & 1u)) mval |= 1u << mi;
+        double* Cw = C + (long)(wrow + r_lane) + (long)(wcol + c_lane) * g.ld;
+
+        // the producer's request for chunk cl of this tile (ring position G)
+        auto issue = [&](int cl, int G) {
+            if (!allReady && (cl & 3) == 0) {
+                wait_flag(fLi + (cl >> 2));
+                if (!diag) wait_flag(fLj + (cl >> 2));
+            }
+            const int sn = G % STAGES;
+            if (G >= STAGES) mbar_wait(emptyB + 8 * sn, ((G / STAGES) - 1) & 1);
+            mbar_expect_tx(fullB + 8 * sn, STAGE_TX);
+            const uint32_t dst = sbase + (uint32_t)(sn * STAGE * 8);
+            tma_load_3d(dst, &mapM, fullB + 8 * sn, rowBase, cl * KC, b);
+            tma_load_3d(dst + OPER * 8, &mapM, fullB + 8 * sn, colBase, cl * KC, b);
+        };
+        if (producer) {
+            // the ring's memory was last touched by ordinary loads and stores (the previous tile's hand-over)
+            asm volatile("fence.proxy.async;\n" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < STAGES - 1; ++s)
+                if (s < nchunks) issue(s, gc + s);
+        }
+
+        double acc[4][8][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+        if (active) {
+            if (full) {
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        acc[mi][ni][0] = __ldcs(&Cw[mi * 8 + (long)(ni * 8) * g.ld]);
+                        acc[mi][ni][1] = __ldcs(&Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld]);
+                    }
+            } else {
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+                        if ((rmask >> mi) & 1u) {
+                            acc[mi][ni][0] = Cw[mi * 8 + (long)(ni * 8) * g.ld];
+                            acc[mi][ni][1] = Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld];
+                        }
+            }
+        }
+
+        // ---- acc -= L(i, 0:j) L(j, 0:j)'
+        for (int c = 0; c < nchunks; ++c, ++gc) {
+            const int s = gc % STAGES;
+            mbar_wait(fullB + 8 * s, (gc / STAGES) & 1);
+            const bool doCopy = c + STAGES - 1 < nchunks;
+            const double* As = smem + s * STAGE + aoff;
+            const double* Bs = smem + s * STAGE + OPER + boff;
+#pragma unroll
+            for (int kk = 0; kk < KC / 4; ++kk) {
+                if (kk == KC / 8 && producer && doCopy) issue(c + STAGES - 1, gc + STAGES - 1);
+                if (active) {
+                    double a[4], bb[8];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const double v = As[kk * 4 * PITCH + mi * 8];
+                        a[mi] = __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v));   // C -= A B'
+                    }
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[kk * 4 * PITCH + ni * 8];
+                    if (mval == 0xFu) {
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                            for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                    } else {
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            if ((mval >> mi) & 1u) {
+#pragma unroll
+                                for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                            }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyB + 8 * s);
+        }
+        __syncthreads();     // every warp has left the ring
+
+        // ---- hand the tile over in shared memory: [column][132 rows] -- potf2's T, and the solve's A operand ([k][row])
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = wm * 32 + mi * 8 + r_lane, c = wn * 64 + ni * 8 + c_lane + h;
+                    smem[c * PITCH + r] = (diag && r < c) ? 0.0 : acc[mi][ni][h];
+                }
+
+        if (diag) {
+            __syncthreads();
+            diag_epilogue(smem, pbar, g.info ? g.info + b : nullptr, colBase, C + (long)colBase + (long)colBase * g.ld, g.ld,
+                          g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE);
+            __threadfence();
+            __syncthreads();
+            if (producer) st_release(g.flagW + (long)b * g.T + j, 1);
+        } else {
+            // ---- L(i,j) = acc W_j'   (W_j lower triangular: columns < 64 need k < 64 only, as in the panel-solve launch)
+            const uint32_t wslab = sbase + (uint32_t)(2 * STAGE * 8);
+            if (producer) {
+                wait_flag(g.flagW + (long)b * g.T + j);
+#pragma unroll
+                for (int cw = 0; cw < 2; ++cw) {
+                    mbar_expect_tx(wfullB + 8 * cw, SLAB_TX);
+                    tma_load_3d(wslab + (uint32_t)(cw * OPER * 8), &mapW, wfullB + 8 * cw, 0, j * FGP_TILE + cw * KC, b);
+                }
+            }
+            __syncthreads();     // hand-over tile complete
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll 1
+            for (int cw = 0; cw < FGP_TILE / KC; ++cw) {
+                mbar_wait(wfullB + 8 * (cw & 1), (cw >> 1) & 1);
+                const bool mult = active && !(cw * KC >= (wn + 1) * 64);
+                const double* As = smem + cw * KC * PITCH + aoff;
+                const double* Bs = smem + 2 * STAGE + (cw & 1) * OPER + boff;
+                if (mult) {
+#pragma unroll
+                    for (int kk = 0; kk < KC / 4; ++kk) {
+                        double a[4], bb[8];
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) a[mi] = As[kk * 4 * PITCH + mi * 8];
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[kk * 4 * PITCH + ni * 8];
+                        if (mval == 0xFu) {
+#pragma unroll
+                            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                        } else {
+#pragma unroll
+                            for (int mi = 0; mi < 4; ++mi)
+                                if ((mval >> mi) & 1u) {
+#pragma unroll
+                                    for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                                }
+                        }
+                    }
+                }
+                __syncthreads();     // slab cw & 1 is free again
+                if (producer && cw + 2 < FGP_TILE / KC) {
+                    mbar_expect_tx(wfullB + 8 * (cw & 1), SLAB_TX);
+                    tma_load_3d(wslab + (uint32_t)((cw & 1) * OPER * 8), &mapW, wfullB + 8 * (cw & 1), 0, j * FGP_TILE + (cw + 2) * KC, b);
+                }
+            }
+            if (active) {
+                if (full) {
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) {
+                            Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
+                            Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
+                        }
+                } else {
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                            if ((rmask >> mi) & 1u) {
+                                Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
+                                Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
+                            }
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (producer) st_release(g.flagL + ((long)b * R + i) * g.T + j, 1);
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+// 3-D map over a column-major operand: (rows, k, batch element); box = PITCH rows x KC k x 1
+bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, long batch, long strideElems) {
+    cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)K, (cuuint64_t)std::max<long>(1, batch)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(batch > 1 ? strideElems : (long)ld * K) * 8};
+    cuuint32_t box[3] = {(cuuint32_t)PITCH, (cuuint32_t)KC, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (strides[1] == 0 || (strides[1] & 15)) strides[1] = (cuuint64_t)ld * 8 * (cuuint64_t)std::max<long>(1, K);
+    return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool chol_dag_supported(int n, int nrows) { return n > 0 && n % FGP_TILE == 0 && nrows == n + 1; }
+
+size_t chol_dag_flag_bytes(int n, int batch) {
+    const size_t T = (size_t)n / FGP_TILE, R = T + 1;
+    return sizeof(int) * ((size_t)batch * R * T + (size_t)batch * T + 4);
+}
+
+// Factors the `batch` trapezoids at M (n columns, n + 1 rows: the y row rides along, leading dimension ld) in place, W
+// receives the inverse diagonal blocks, info the failing minor orders.  flags: chol_dag_flag_bytes() of device memory.
+// Returns false when the launch cannot be taken (driver entry point missing, alignment) -- the caller then runs chol.cu.
+bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
+                     cudaStream_t st) {
+    static bool attr_set[FGP_MAXDEV] = {false};
+    static int nsm[FGP_MAXDEV] = {0};
+    if (!chol_dag_supported(n, n + 1) || batch <= 0) return false;
+    if (!g_encode_tried) {
+        g_encode_tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+        else cudaGetLastError();
+    }
+    if (!g_encode) return false;
+    if (((uintptr_t)M & 15) || ((uintptr_t)W & 15) || (ld & 1) || (strideM & 1) || (strideW & 1)) return false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= FGP_MAXDEV) dev = 0;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
+        attr_set[dev] = true;
+    }
+    DagArgs g{};
+    g.M = M; g.ld = ld; g.strideM = strideM; g.batch = batch;
+    g.T = n / FGP_TILE; g.R = g.T + 1; g.nrows = n + 1;
+    g.W = W; g.strideW = strideW; g.info = info;
+    const size_t nL = (size_t)batch * g.R * g.T, nW = (size_t)batch * g.T;
+    g.flagL = (int*)flags; g.flagW = g.flagL + nL; g.counter = g.flagW + nW;
+    const long perMatrix = (long)g.T * g.R - (long)g.T * (g.T - 1) / 2;
+    if (perMatrix * batch > 0x7fffffffL / 2) return false;
+    g.ntasks = (int)(perMatrix * batch);
+    CUtensorMap mapM, mapW;
+    if (!make_map(&mapM, M, g.nrows, n, ld, batch, strideM)) return false;
+    if (!make_map(&mapW, W, FGP_TILE, (long)g.T * FGP_TILE, FGP_TILE, batch, strideW)) return false;
+    if (cudaMemsetAsync(flags, 0, chol_dag_flag_bytes(n, batch), st) != cudaSuccess) { cudaGetLastError(); return false; }
+    const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
+    FGP_COUNT_LAUNCH();
+    chol_dag_kernel<<<std::min(sms, g.ntasks), THREADS, DAG_SMEM, st>>>(g, mapM, mapW);
+    return cudaGetLastError() == cudaSuccess;
+}

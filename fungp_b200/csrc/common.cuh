@@ -111,6 +111,12 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
 void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, double* W, long strideW, int* info,
                   int infoBase, cudaStream_t st, int pdl = 0);
 
+// the whole factorisation of a batch as one persistent dataflow kernel (chol_dag.cu); n a multiple of 128
+bool chol_dag_supported(int n, int nrows);
+size_t chol_dag_flag_bytes(int n, int batch);
+bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
+                     cudaStream_t st);
+
 struct GemmArgs {
     const double* A; long lda; long strideA;   // row operand: element (r, kk) = A[r + kk*lda], r = global row
     const double* B; long ldb; long strideB;   // col operand: element (c, kk) = B[c + kk*ldb]
