@@ -115,9 +115,14 @@ __device__ __forceinline__ void wait_flag(const int* p) {
 
 // the diagonal tile, handed over in shared memory: factor, store L(j,j) and W_j.  Not inlined: the block algorithm runs at
 // 255 registers on its own and must not share an allocation with the 128 accumulator registers of the tile loop.
-__device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* infoPtr, int infoOff, double* Mdiag, long ld, double* Wb) {
+__device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* infoPtr, int infoOff, double* Mdiag, long ld, double* Wb,
+                                           int* flagW) {
     potf2::factor_block(smem, pbar, infoPtr, infoOff);
-    potf2::store_block(smem, Mdiag, ld, FGP_TILE, Wb);
+    potf2::store_W(smem, Wb);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flagW, 1);        // the solves of this column may start; L(j,j) itself is read by nobody here
+    potf2::store_L(smem, Mdiag, ld, FGP_TILE);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -299,10 +304,8 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         if (diag) {
             __syncthreads();
             diag_epilogue(smem, pbar, g.info ? g.info + b : nullptr, colBase, C + (long)colBase + (long)colBase * g.ld, g.ld,
-                          g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE);
-            __threadfence();
-            __syncthreads();
-            if (producer) st_release(g.flagW + (long)b * g.T + j, 1);
+                          g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE, g.flagW + (long)b * g.T + j);
+            __syncthreads();     // the hand-over area is free again
         } else {
             // ---- L(i,j) = acc W_j'   (W_j lower triangular: columns < 64 need k < 64 only, as in the panel-solve launch)
             const uint32_t wslab = sbase + (uint32_t)(2 * STAGE * 8);

@@ -45,7 +45,7 @@ struct Cand {
 struct Lane {
     cudaStream_t st[DevState::MAXSTREAMS] = {nullptr};
     cudaEvent_t evFork = nullptr, evJoin[DevState::MAXSTREAMS] = {nullptr}, evDone = nullptr;
-    DevBuf work, wbuf, blob, res, lwork, lwbuf;
+    DevBuf work, wbuf, blob, res, lwork, lwbuf, dag;     // dag: flags + task counter of the dataflow Cholesky, per lane
     char* hBlob = nullptr; size_t hBlobCap = 0;
     char* hRes = nullptr; size_t hResCap = 0;
     std::vector<Cand*> cands;
@@ -87,7 +87,7 @@ void lock_free(void* p) {
         }
         if (ln.evFork) cudaEventDestroy(ln.evFork);
         if (ln.evDone) cudaEventDestroy(ln.evDone);
-        ln.work.release(); ln.wbuf.release(); ln.blob.release(); ln.res.release(); ln.lwork.release(); ln.lwbuf.release();
+        ln.work.release(); ln.wbuf.release(); ln.blob.release(); ln.res.release(); ln.lwork.release(); ln.lwbuf.release(); ln.dag.release();
         if (ln.hBlob) cudaFreeHost(ln.hBlob);
         if (ln.hRes) cudaFreeHost(ln.hRes);
     }
@@ -566,7 +566,9 @@ struct Driver {
             }
         }
         // ---- factorisations: groups of slots on the lane's streams (one group below n = 2048)
-        const int ns = B > 0 ? std::max(1, std::min(nst, B)) : 0;
+        // (dataflow Cholesky: all slots of the round in one persistent launch on the lane's first stream)
+        const bool useDag = B > 0 && (wc->dag >= 2 || (wc->dag == 1 && n >= 2048)) && !wc->profile && chol_dag_supported(n, n + 1) && !ln.dag.ensure(chol_dag_flag_bytes(n, B));
+        const int ns = B > 0 ? (useDag ? 1 : std::max(1, std::min(nst, B))) : 0;
         if (ns > 1) LCK(cudaEventRecord(ln.evFork, s0));
         const int per = ns ? cdiv(B, ns) : 0;
         for (int s = 0; s < ns; ++s) {
@@ -581,8 +583,10 @@ struct Driver {
             t.ncols = n; t.nrows = n + 1; t.holeLo = n + 1; t.holeHi = n + 1; t.colHoleLo = n; t.colHoleHi = n; t.cpre = 0; t.upperRows = 0;
             t.W = (double*)ln.wbuf.p + (size_t)g0 * ncT * FGP_TILE * FGP_TILE; t.strideW = (long)ncT * FGP_TILE * FGP_TILE;
             t.info = dInfo + g0;
-            int rc = trap_factor(wc, 0, t, st, nullptr, false);
-            if (rc) return rc;
+            if (!(useDag && launch_chol_dag(t.M, t.ld, t.strideM, t.batch, n, t.W, t.strideW, t.info, ln.dag.p, st))) {
+                int rc = trap_factor(wc, 0, t, st, nullptr, false);
+                if (rc) return rc;
+            }
             launch_nll_reduce(Mg, ld, (long)ld * n, g1 - g0, n, n, nullptr, dInfo + g0, dNll + g0, dSig + g0, st);
             if (s > 0) {
                 LCK(cudaEventRecord(ln.evJoin[s], st));
@@ -731,7 +735,7 @@ int fit_lockstep(fgp_ctx* ctx, Shared& S, const std::vector<int>& order) {
             cudaSetDevice(device);
             wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
             wc->fit_points = ctx->fit_points; wc->fit_lanes = ctx->fit_lanes; wc->predict_reserve = ctx->predict_reserve;
-            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat;
+            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat; wc->dag = ctx->dag;
             wc->blockingSync = ctx->fit_blocking > 0 ? ctx->fit_blocking : 0;
             // option "profile": per-launch CUDA events of this call's rounds on the first GPU (meaningful with fit_lanes = 1,
             // where the rounds do not overlap); fgp_get_timing on the caller's context reports them

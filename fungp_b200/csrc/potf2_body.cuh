@@ -319,24 +319,15 @@ __device__ __forceinline__ void factor_block(double* sm, uint32_t barAddr, int* 
 
 }
 
-// L -> the lower triangle of the block at Mdiag; W = inv(L) -> Wb (128 x 128 column-major, unit padded)
-__device__ __forceinline__ void store_block(double* sm, double* Mdiag, long ld, int nb, double* Wb) {
+// W = inv(L) -> Wb (128 x 128 column-major, unit padded): what the rest of the factorisation waits for, so it goes first
+__device__ __forceinline__ void store_W(double* sm, double* Wb) {
     double* T = sm;
     double* dinvE = sm + NB * LDT + SB * XLD + SB * ELD;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    double* Mb = Mdiag;
-    const int k0 = 0;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     PROF(13);
-    // ---- write back L (lower triangle of the valid part)
-#pragma unroll 8
-    for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
-        const int r = idx & (NB - 1), c = idx >> 7;
-        if (r >= c && r < nb && c < nb) Mb[(long)(k0 + r) + (long)(k0 + c) * ld] = T[c * LDT + r];
-    }
-    PROF(14);
-    // ---- W = inv(L) (128x128 column-major, unit padded): W(r,c) = E(c,r) = T(row c, col r) for r > c, i.e. T read
+    // ---- W = inv(L) first: it is what the rest of the factorisation waits for
+    // ---- (128x128 column-major, unit padded): W(r,c) = E(c,r) = T(row c, col r) for r > c, i.e. T read
     //      along its leading dimension.  A half-warp takes 4 consecutive r x 4 consecutive c: with LDT = 4 (mod 16) the
     //      sixteen 8-byte words fall into sixteen different bank pairs, and every 4 r of one c are one 32-byte sector.
     for (int it = 0; it < (NB * NB) / (POTF2_THREADS * 1); ++it) {
@@ -348,7 +339,27 @@ __device__ __forceinline__ void store_block(double* sm, double* Mdiag, long ld, 
         else if (r == c) w = dinvE[r];
         Wb[r + c * NB] = w;
     }
+    PROF(14);
+}
+
+// L -> the lower triangle of the block at Mdiag
+__device__ __forceinline__ void store_L(double* sm, double* Mdiag, long ld, int nb) {
+    double* T = sm;
+    const int tid = threadIdx.x;
+    double* Mb = Mdiag;
+    const int k0 = 0;
+    // ---- write back L (lower triangle of the valid part)
+#pragma unroll 8
+    for (int idx = tid; idx < NB * NB; idx += POTF2_THREADS) {
+        const int r = idx & (NB - 1), c = idx >> 7;
+        if (r >= c && r < nb && c < nb) Mb[(long)(k0 + r) + (long)(k0 + c) * ld] = T[c * LDT + r];
+    }
     PROF(15);
+}
+
+__device__ __forceinline__ void store_block(double* sm, double* Mdiag, long ld, int nb, double* Wb) {
+    store_W(sm, Wb);
+    store_L(sm, Mdiag, ld, nb);
 }
 
 }  // namespace potf2

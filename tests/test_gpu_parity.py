@@ -726,3 +726,37 @@ def test_tma_and_cp_async_gemm_kernels_agree_bitwise(ctx):
     r_nll, _ = ref.negLogLik(theta, [], Ms, case["y"], "matern5_2", 1e-8)
     assert abs(out[1][0][0] - r_nll) <= _nll_tol(r_nll, n)
     P.close()
+
+
+@pytest.mark.parametrize("n,B", [(128, 1), (384, 4), (1024, 7), (2560, 3)])
+def test_dataflow_cholesky_is_bit_identical(ctx, n, B):
+    """csrc/chol_dag.cu -- the factorisation of a whole batch as one persistent kernel of tile tasks (left-looking
+    accumulation through the TMA ring, the diagonal block and the triangular solve as epilogues, ready flags between
+    CTAs) -- against the launch-per-step engine of csrc/chol.cu: the same DMMA sequence per entry, so likelihoods, the
+    stored factor, L^-1 y and everything computed from them agree to the last bit; and against the oracle.  Also: a
+    matrix that is not positive definite reports the same minor and does not stall the kernel."""
+    seed, m = 300 + n, 40
+    case = make_case(seed, n, 2, [25, 18], [3, 2], ["B-splines", "PCA"], ["L2_bygroup", "L2_byindex"], extra=m)
+    P = _problem(ctx, case)
+    ub = 2.0 * P.dist_max()
+    thB = np.stack([0.3 * ub * (1 + 0.05 * i) for i in range(B)], axis=1)
+    out = {}
+    try:
+        for dag in (0, 1):
+            ctx.set_option("dag", dag)
+            nll, s2, info = P.nll_batch("matern3_2", 1e-8, thB)
+            assert not info.any()
+            L, z = P.premats("matern3_2", 1e-8, s2[0], thB[:, 0])
+            pr = P.predict(m, case["sNew"], case["coefsNew"])
+            # nugget -1e-3: indefinite where the correlations are close to 1 (first point), fine where they are close to 0
+            bad = P.nll_batch("gauss", -1e-3, np.stack([40.0 * ub, 0.01 * ub], axis=1))
+            out[dag] = (nll, s2, L, z, pr["mean"], pr["sd"], bad[2], bad[0][1:])
+    finally:
+        ctx.set_option("dag", 1)
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert out[1][6][0] > 0 and out[1][6][1] == 0
+    Ms = oracle_dists(case)
+    r_nll, _ = ref.negLogLik(thB[:, 0], [], Ms, case["y"], "matern3_2", 1e-8)
+    assert abs(out[1][0][0] - r_nll) <= _nll_tol(r_nll, n)
+    P.close()

@@ -1,5 +1,5 @@
 """Factory arm of bench.py under different driver options (GPU box): candidates/s, likelihood evaluations/s, TFLOP/s.
-usage: python tools/factory_probe2.py N_CAND  [mode:points:lanes[:fused_assembly[:gemm_flat]] ...]   e.g.  512 1:512:2 1:256:2 1:1024:1 0:0:0"""
+usage: python tools/factory_probe2.py N_CAND  [mode:points:lanes[:fused_assembly[:gemm_flat[:dag]]] ...]   e.g.  512 1:512:2 1:256:2 1:1024:1 0:0:0"""
 import json
 import os
 import sys
@@ -26,6 +26,7 @@ for cfg in configs:
     mode, pts, lanes = parts[:3]
     fusedA = parts[3] if len(parts) > 3 else 1
     ctx.set_option("gemm_flat", parts[4] if len(parts) > 4 else 8)
+    ctx.set_option("dag", parts[5] if len(parts) > 5 else 0)
     ctx.set_option("fit_mode", mode); ctx.set_option("fit_points", pts); ctx.set_option("fit_lanes", lanes)
     ctx.set_option("fused_assembly", fusedA)
     if mode == 0:
