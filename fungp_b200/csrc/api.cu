@@ -144,7 +144,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "host_threads")) ctx->host_threads = std::max(0, std::min((int)value, 64));
     else if (!strcmp(name, "out_prezeroed")) ctx->out_prezeroed = value != 0 ? 1 : 0;
     else if (!strcmp(name, "host_thp")) ctx->host_thp = value != 0 ? 1 : 0;
-    else if (!strcmp(name, "dag")) ctx->dag = std::max(0, std::min((int)value, 2));
+    else if (!strcmp(name, "dag")) ctx->dag = value != 0 ? 1 : 0;
     else if (!strcmp(name, "gemm_flat")) ctx->gemm_flat = value < 0 ? 0 : (int)value;
     else if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value != 0 ? 1 : 0; g_plain_tma = ctx->gemm_tma; }
     else if (!strcmp(name, "fused_assembly")) ctx->fused_assembly = value != 0 ? 1 : 0;

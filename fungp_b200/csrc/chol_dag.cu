@@ -1,26 +1,31 @@
 // The whole blocked Cholesky of a batch of (n + 1)-row trapezoids as ONE persistent dataflow kernel.
 //
-// Replaces, for the likelihood path (base::chol + backsolve of R/3_training_SF.R:249,267), the launch sequence of
-// chol.cu -- per column tile: diagonal-block kernel, panel-solve GEMM, one or more trailing-update GEMMs -- by a single
-// launch of one CTA per SM.  The unit of work is one 128x128 tile (i, j) of one matrix, done left-looking by ONE CTA
-// from start to finish:
+// Replaces, for the likelihood path (base::chol + backsolve of R/3_training_SF.R:249,267) and preMats
+// (R/3_training_SF.R:262-267), the launch sequence of chol.cu -- per column tile: diagonal-block kernel, panel-solve
+// GEMM, one or more trailing-update GEMMs -- by a single launch of one CTA per SM.  The unit of work is one 128x128
+// tile (i, j) of one matrix, done left-looking by ONE CTA from start to finish:
 //     acc  = A(i,j)                                      the assembled tile, read once
 //     acc -= L(i, 0:j) L(j, 0:j)'                        K = 128 j through the TMA ring of gemm_tma.cu; a k-tile kt is
 //                                                        requested as soon as L(i,kt) and L(j,kt) are flagged ready
-//     i == j :  L(j,j), W_j = potf2(acc)                 potf2_body.cuh on the tile handed over in shared memory
-//     i >  j :  L(i,j) = acc W_j'                        once W_j is flagged; DMMA from shared memory
-//     store, __threadfence, flag (i,j) / W_j ready
+//     i == j :  L(j,j), W_j = potf2(acc)                 potf2_body.cuh on the tile handed over in shared memory;
+//               (L^-1 y)_j                               the y row rides along: the two warps of a diagonal tile that lie
+//                                                        above the diagonal update it with FMAs in k order on the slabs
+//                                                        passing through the ring, and it is solved against W_j here
+//     i >  j :  L(i,j) = acc W_j'                        once W_j is flagged; DMMA from shared memory, zero blocks skipped
+//     store, __threadfence, flag (i,j) / W_j / y_j ready
 // Tiles are claimed from one atomic counter in an order in which every tile's inputs have smaller numbers -- column by
 // column, inside a column the diagonal tiles of all matrices first, then row by row over the matrices -- so a CTA only
-// ever waits for tiles that are already running or done on other resident CTAs: no deadlock whatever the number of
-// resident CTAs.  Why: (1) the chain diagonal block -> solve -> next diagonal block is walked at flag latency (~1-2 us)
-// instead of three kernel launches per column, and the CTAs holding later tiles fill in behind it; (2) every C tile is
-// read and written once instead of once per panel level; (3) batches of small matrices need one launch per round.
-// Numerics: per entry the same DMMA sequence in the same k order as the launch-per-step engine (whose updates also
-// accumulate k ascending, merely interrupted by exact stores and loads), the same potf2 code, the same zero-skipping in
-// the solve: results are bit-identical (tests/test_gpu_parity.py::test_dataflow_cholesky_is_bit_identical).
-// Scope: n a multiple of 128 (the y row then sits alone in row tile n / 128), no holes, nothing prefactored;
-// everything else stays on chol.cu.
+// ever waits for tiles that are already running or done on other resident CTAs (or claimed by a CTA that is finishing a
+// tile with a smaller number): no deadlock whatever the number of resident CTAs.  Why: (1) the chain diagonal block ->
+// solve -> next diagonal block is walked at flag latency (~1-2 us) instead of three kernel launches per column, and the
+// CTAs holding later tiles fill in behind it; (2) every C tile is read and written once instead of once per panel
+// level; (3) batches of small matrices need one launch per round; (4) no separate one-row tiles for y.
+// Numerics: per entry the same sequence of fused multiply-adds in the same k order as the launch-per-step engine (whose
+// updates also accumulate k ascending, merely interrupted by exact stores and loads; one FP64 DMMA m8n8k4 is four
+// chained FMAs in k order, tools/dmma_order.cu), the same potf2 code; only products with exact zeros of W_j are left
+// out: results are bit-identical (tests/test_gpu_parity.py::test_dataflow_cholesky_is_bit_identical).
+// Scope: n a multiple of 128 (all tiles full, the y row is row n), no holes, nothing prefactored; everything else
+// (ragged n, predict / simulate / LOOCV / update trapezoids) stays on chol.cu.
 #include "potf2_body.cuh"
 #include <cuda.h>
 #include <algorithm>
@@ -41,18 +46,20 @@ constexpr int BAR_OFF = RING_BYTES;                     // full[3] | empty[3]
 constexpr int WBAR_OFF = BAR_OFF + 64;                  // wfull[2]: the two W slabs of the solve
 constexpr int PBAR_OFF = WBAR_OFF + 16;                 // potf2's 32 column barriers
 constexpr int TASK_OFF = PBAR_OFF + 8 * potf2::SB;
-constexpr int DAG_SMEM = TASK_OFF + 16;
+constexpr int AY_OFF = TASK_OFF + 16;                   // the y row of the diagonal tile in flight (128 doubles)
+constexpr int DAG_SMEM = AY_OFF + 8 * FGP_TILE;
 static_assert(potf2::POTF2_WORK_DOUBLES * 8 <= RING_BYTES, "potf2 works inside the ring's memory");
 static_assert(potf2::NB * potf2::LDT * 8 == 2 * STAGE * 8, "hand-over tile = stages 0 and 1");
 static_assert(potf2::LDT == PITCH, "one layout for the hand-over tile, potf2's T and the solve's A operand");
 
 struct DagArgs {
     double* M; long ld; long strideM;
-    int batch, T, R, nrows;        // T column tiles, R = T + 1 row tiles, nrows = 128 T + 1
+    int batch, T, n;               // T = n / 128 tile rows and columns; the y row (row n) rides along in the diagonal tasks
     double* W; long strideW;
     int* info;
-    int* flagL;                    // [batch][R][T]  L(i,j) stored
-    int* flagW;                    // [batch][T]     W_j (and L(j,j)) stored
+    int* flagL;                    // [batch][T][T]  L(i,j) stored
+    int* flagW;                    // [batch][T]     W_j stored
+    int* flagY;                    // [batch][T]     (L^-1 y) of column tile j stored
     int* counter;
     int ntasks;
 };
@@ -113,15 +120,30 @@ __device__ __forceinline__ void wait_flag(const int* p) {
     asm volatile("fence.proxy.async;\n" ::: "memory");
 }
 
-// the diagonal tile, handed over in shared memory: factor, store L(j,j) and W_j.  Not inlined: the block algorithm runs at
-// 255 registers on its own and must not share an allocation with the 128 accumulator registers of the tile loop.
+// The diagonal tile, handed over in shared memory: factor it, store W_j and flag it (the solves of the column start), then
+// the y row of this column tile -- y_out(c) = sum_{k <= c} ay(k) W_j(c, k), the chain of FMAs in k order that the DMMA
+// solve of the launch-per-step engine performs (one m8n8k4 DMMA IS four chained FMAs in k order, tools/dmma_order.cu) --
+// then L(j,j).  Not inlined: the block algorithm runs at 255 registers on its own and must not share an allocation with
+// the 128 accumulator registers of the tile loop.
 __device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* infoPtr, int infoOff, double* Mdiag, long ld, double* Wb,
-                                           int* flagW) {
+                                           int* flagW, const double* ay, double* yOut, int* flagY) {
     potf2::factor_block(smem, pbar, infoPtr, infoOff);
     potf2::store_W(smem, Wb);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) st_release(flagW, 1);        // the solves of this column may start; L(j,j) itself is read by nobody here
+    if (threadIdx.x == 0) st_release(flagW, 1);
+    if (threadIdx.x < FGP_TILE) {
+        const int c = threadIdx.x;
+        const double* Tc = smem + c * potf2::LDT;                 // strict upper part of column c: E(k, c) = W(c, k), k < c
+        const double* dinvE = smem + potf2::NB * potf2::LDT + potf2::SB * potf2::XLD + potf2::SB * potf2::ELD;
+        double sacc = 0.0;
+        for (int k = 0; k < c; ++k) sacc = fma(ay[k], Tc[k], sacc);
+        sacc = fma(ay[c], dinvE[c], sacc);
+        yOut[(long)c * ld] = sacc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flagY, 1);
     potf2::store_L(smem, Mdiag, ld, FGP_TILE);
 }
 
@@ -137,6 +159,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
     const uint32_t wfullB = sbase + WBAR_OFF;
     const uint32_t pbar = sbase + PBAR_OFF;
     volatile int* sTask = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(smem) + TASK_OFF);
+    double* ay = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + AY_OFF);
     const bool producer = tid == 0;
     if (producer) {
 #pragma unroll
@@ -145,6 +168,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapM)) : "memory");
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapW)) : "memory");
+        sTask[0] = atomicAdd(g.counter, 1);
     }
     potf2::init_barriers(pbar);
     __syncthreads();
@@ -156,53 +180,52 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
     const int c_lane = 2 * (lane & 3);
     const int aoff = (lane & 3) * PITCH + wm * 32 + r_lane;
     const int boff = (lane & 3) * PITCH + wn * 64 + r_lane;
-    const int B = g.batch, R = g.R;
+    const int B = g.batch, T = g.T;
+    // With several matrices in flight a CTA claims its next tile while it finishes the current one (the atomic's round trip
+    // hides under the epilogue).  With few, idle CTAs are waiting for exactly such a tile: claim only when free.
+    const bool claimAhead = B >= 4;
 
     int gc = 0;   // chunks this CTA has sent through the ring so far (ring position and barrier phases)
-    for (;;) {
-        if (producer) *sTask = atomicAdd(g.counter, 1);
-        __syncthreads();
-        const int task = *sTask;
-        if (task >= g.ntasks) break;
-        // column j holds B (R - j) tasks; tasks before column j: B (j R - j (j - 1) / 2)
+    int task = sTask[0];
+    for (int it = 0; task < g.ntasks; ++it) {
+        // column j holds B (T - j) tasks -- the B diagonal tiles, then row by row; before column j: B (j T - j (j - 1) / 2)
         const int q = task / B;
-        int j = (int)(((float)(2 * R + 1) - sqrtf((float)(2 * R + 1) * (float)(2 * R + 1) - 8.0f * (float)q)) * 0.5f);
-        j = max(0, min(j, g.T - 1));
-        while (j + 1 < g.T && (j + 1) * R - (j + 1) * j / 2 <= q) ++j;
-        while (j > 0 && j * R - j * (j - 1) / 2 > q) --j;
-        const int local = task - B * (j * R - j * (j - 1) / 2);
+        int j = (int)(((float)(2 * T + 1) - sqrtf((float)(2 * T + 1) * (float)(2 * T + 1) - 8.0f * (float)q)) * 0.5f);
+        j = max(0, min(j, T - 1));
+        while (j + 1 < T && (j + 1) * T - (j + 1) * j / 2 <= q) ++j;
+        while (j > 0 && j * T - j * (j - 1) / 2 > q) --j;
+        const int local = task - B * (j * T - j * (j - 1) / 2);
         const int i = j + local / B;
         const int b = local - (local / B) * B;
         const bool diag = i == j;
         const int rowBase = i * FGP_TILE, colBase = j * FGP_TILE;
         double* C = g.M + (long)b * g.strideM;
-        const int* fLi = g.flagL + ((long)b * R + i) * g.T;
-        const int* fLj = g.flagL + ((long)b * R + j) * g.T;
+        const int* fLi = g.flagL + ((long)b * T + i) * T;
+        const int* fLj = g.flagL + ((long)b * T + j) * T;
+        const int* fY = g.flagY + (long)b * T;
         const int nchunks = j * (FGP_TILE / KC);
         // Are all inputs of this tile there already?  (The usual case away from the start and the end of the
-        // factorisation.)  Then the producer never polls; otherwise it waits k-tile by k-tile as they are flagged.
+        // factorisation.)  Then nobody polls; otherwise the producer waits k-tile by k-tile as they are flagged.
         bool ready = true;
         for (int kt = tid; kt < j; kt += THREADS) {
             ready = ready && ld_acquire(fLi + kt) != 0;
             if (!diag) ready = ready && ld_acquire(fLj + kt) != 0;
+            else ready = ready && ld_acquire(fY + kt) != 0;
         }
-        const bool allReady = __syncthreads_and(ready) != 0;      // also: everybody has read the task slot
+        const bool allReady = __syncthreads_and(ready) != 0;
 
-        const int wrow = rowBase + wm * 32;
-        const int wcol = colBase + wn * 64;
-        unsigned rmask = 0;
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-            if (wrow + mi * 8 + r_lane < g.nrows) rmask |= 1u << mi;
-        bool active = __any_sync(0xffffffffu, rmask != 0);
-        if (diag && (wm * 32 + 31 < wn * 64)) active = false;        // warps entirely above the diagonal
-        if (!active) rmask = 0;
-        const bool full = __all_sync(0xffffffffu, rmask == 0xFu);
-        unsigned mval = 0;
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-            if (__any_sync(0xffffffffu, (rmask >> mi) & 1u)) mval |= 1u << mi;
-        double* Cw = C + (long)(wrow + r_lane) + (long)(wcol + c_lane) * g.ld;
+        // diagonal tiles: the two warps that lie entirely above the diagonal carry the y row instead -- 64 columns each,
+        // two per lane: ay(c) -= sum_k y(k) L(j-tile row c, k), FMAs in k order on the B slabs that pass through the ring
+        const bool active = !(diag && (wm * 32 + 31 < wn * 64));
+        const bool ywarp = diag && !active;
+        const int ycol = (wm == 0 ? 0 : 64) + lane;
+        const double* yrow = C + g.n;                                    // element k of the y row: yrow[k * ld]
+        double ay0 = 0.0, ay1 = 0.0;
+        if (ywarp) {
+            ay0 = __ldcg(yrow + (long)(colBase + ycol) * g.ld);
+            ay1 = __ldcg(yrow + (long)(colBase + ycol + 32) * g.ld);
+        }
+        double* Cw = C + (long)(rowBase + wm * 32 + r_lane) + (long)(colBase + wn * 64 + c_lane) * g.ld;
 
         // the producer's request for chunk cl of this tile (ring position G)
         auto issue = [&](int cl, int G) {
@@ -226,38 +249,48 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         }
 
         double acc[4][8][2];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
         if (active) {
-            if (full) {
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni)
+            for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) {
-                        acc[mi][ni][0] = __ldcs(&Cw[mi * 8 + (long)(ni * 8) * g.ld]);
-                        acc[mi][ni][1] = __ldcs(&Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld]);
-                    }
-            } else {
+                for (int mi = 0; mi < 4; ++mi) {
+                    acc[mi][ni][0] = __ldcs(&Cw[mi * 8 + (long)(ni * 8) * g.ld]);
+                    acc[mi][ni][1] = __ldcs(&Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld]);
+                }
+        } else {
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni)
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi)
-                        if ((rmask >> mi) & 1u) {
-                            acc[mi][ni][0] = Cw[mi * 8 + (long)(ni * 8) * g.ld];
-                            acc[mi][ni][1] = Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld];
-                        }
-            }
+                for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
         }
 
         // ---- acc -= L(i, 0:j) L(j, 0:j)'
         for (int c = 0; c < nchunks; ++c, ++gc) {
             const int s = gc % STAGES;
+            double yk = 0.0;
+            if (ywarp) {
+                if (!allReady && (c & 3) == 0) {
+                    const long long t0 = clock64();
+                    while (ld_acquire(fY + (c >> 2)) == 0) {
+                        __nanosleep(64);
+                        if (clock64() - t0 > SPIN_LIMIT_CLOCKS) __trap();
+                    }
+                }
+                yk = __ldcg(yrow + (long)(c * KC + lane) * g.ld);       // solved y entries of this chunk's 32 columns
+            }
             mbar_wait(fullB + 8 * s, (gc / STAGES) & 1);
             const bool doCopy = c + STAGES - 1 < nchunks;
             const double* As = smem + s * STAGE + aoff;
             const double* Bs = smem + s * STAGE + OPER + boff;
+            if (ywarp) {
+                const double* Bc = smem + s * STAGE + OPER + ycol;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const double yv = -__shfl_sync(0xffffffffu, yk, k);
+                    ay0 = fma(yv, Bc[k * PITCH], ay0);
+                    ay1 = fma(yv, Bc[k * PITCH + 32], ay1);
+                }
+            }
 #pragma unroll
             for (int kk = 0; kk < KC / 4; ++kk) {
                 if (kk == KC / 8 && producer && doCopy) issue(c + STAGES - 1, gc + STAGES - 1);
@@ -270,25 +303,17 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                     }
 #pragma unroll
                     for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[kk * 4 * PITCH + ni * 8];
-                    if (mval == 0xFu) {
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi)
+                    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                            for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
-                    } else {
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi)
-                            if ((mval >> mi) & 1u) {
-#pragma unroll
-                                for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
-                            }
-                    }
+                        for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(emptyB + 8 * s);
         }
         __syncthreads();     // every warp has left the ring
+        if (producer && claimAhead) sTask[(it + 1) & 1] = atomicAdd(g.counter, 1);
 
         // ---- hand the tile over in shared memory: [column][132 rows] -- potf2's T, and the solve's A operand ([k][row])
 #pragma unroll
@@ -302,15 +327,18 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                 }
 
         if (diag) {
+            if (ywarp) { ay[ycol] = ay0; ay[ycol + 32] = ay1; }
             __syncthreads();
             diag_epilogue(smem, pbar, g.info ? g.info + b : nullptr, colBase, C + (long)colBase + (long)colBase * g.ld, g.ld,
-                          g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE, g.flagW + (long)b * g.T + j);
+                          g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE, g.flagW + (long)b * T + j, ay,
+                          C + g.n + (long)colBase * g.ld, g.flagY + (long)b * T + j);
             __syncthreads();     // the hand-over area is free again
         } else {
-            // ---- L(i,j) = acc W_j'   (W_j lower triangular: columns < 64 need k < 64 only, as in the panel-solve launch)
+            // ---- L(i,j) = acc W_j'   (W_j lower triangular: W(c, k) = 0 for k > c, so an 8-column block of the result
+            //      needs k up to its last column only -- the zero products are skipped, block by block)
             const uint32_t wslab = sbase + (uint32_t)(2 * STAGE * 8);
             if (producer) {
-                wait_flag(g.flagW + (long)b * g.T + j);
+                wait_flag(g.flagW + (long)b * T + j);
 #pragma unroll
                 for (int cw = 0; cw < 2; ++cw) {
                     mbar_expect_tx(wfullB + 8 * cw, SLAB_TX);
@@ -325,31 +353,24 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 #pragma unroll 1
             for (int cw = 0; cw < FGP_TILE / KC; ++cw) {
                 mbar_wait(wfullB + 8 * (cw & 1), (cw >> 1) & 1);
-                const bool mult = active && !(cw * KC >= (wn + 1) * 64);
                 const double* As = smem + cw * KC * PITCH + aoff;
                 const double* Bs = smem + 2 * STAGE + (cw & 1) * OPER + boff;
-                if (mult) {
 #pragma unroll
-                    for (int kk = 0; kk < KC / 4; ++kk) {
-                        double a[4], bb[8];
+                for (int kk = 0; kk < KC / 4; ++kk) {
+                    // result columns below k0 = cw*32 + kk*4 only meet zeros of W from here on
+                    const int niSkip = (cw * KC + kk * 4 - wn * 64) >> 3;       // arithmetic shift: negative = nothing to skip
+                    if (niSkip >= 8) continue;
+                    double a[4], bb[8];
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) a[mi] = As[kk * 4 * PITCH + mi * 8];
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = As[kk * 4 * PITCH + mi * 8];
 #pragma unroll
-                        for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[kk * 4 * PITCH + ni * 8];
-                        if (mval == 0xFu) {
+                    for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[kk * 4 * PITCH + ni * 8];
 #pragma unroll
-                            for (int mi = 0; mi < 4; ++mi)
+                    for (int ni = 0; ni < 8; ++ni)
+                        if (ni >= niSkip) {
 #pragma unroll
-                                for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
-                        } else {
-#pragma unroll
-                            for (int mi = 0; mi < 4; ++mi)
-                                if ((mval >> mi) & 1u) {
-#pragma unroll
-                                    for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
-                                }
+                            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
                         }
-                    }
                 }
                 __syncthreads();     // slab cw & 1 is free again
                 if (producer && cw + 2 < FGP_TILE / KC) {
@@ -357,30 +378,20 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                     tma_load_3d(wslab + (uint32_t)((cw & 1) * OPER * 8), &mapW, wfullB + 8 * (cw & 1), 0, j * FGP_TILE + (cw + 2) * KC, b);
                 }
             }
-            if (active) {
-                if (full) {
 #pragma unroll
-                    for (int ni = 0; ni < 8; ++ni)
+            for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) {
-                            Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
-                            Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
-                        }
-                } else {
-#pragma unroll
-                    for (int ni = 0; ni < 8; ++ni)
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi)
-                            if ((rmask >> mi) & 1u) {
-                                Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
-                                Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
-                            }
+                for (int mi = 0; mi < 4; ++mi) {
+                    Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
+                    Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
                 }
-            }
             __threadfence();
             __syncthreads();
-            if (producer) st_release(g.flagL + ((long)b * R + i) * g.T + j, 1);
+            if (producer) st_release(g.flagL + ((long)b * T + i) * T + j, 1);
         }
+        if (producer && !claimAhead) sTask[(it + 1) & 1] = atomicAdd(g.counter, 1);
+        __syncthreads();
+        task = sTask[(it + 1) & 1];
     }
 }
 
@@ -405,8 +416,8 @@ bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, lo
 bool chol_dag_supported(int n, int nrows) { return n > 0 && n % FGP_TILE == 0 && nrows == n + 1; }
 
 size_t chol_dag_flag_bytes(int n, int batch) {
-    const size_t T = (size_t)n / FGP_TILE, R = T + 1;
-    return sizeof(int) * ((size_t)batch * R * T + (size_t)batch * T + 4);
+    const size_t T = (size_t)n / FGP_TILE;
+    return sizeof(int) * ((size_t)batch * T * T + 2 * (size_t)batch * T + 4);
 }
 
 // Factors the `batch` trapezoids at M (n columns, n + 1 rows: the y row rides along, leading dimension ld) in place, W
@@ -440,15 +451,15 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
     }
     DagArgs g{};
     g.M = M; g.ld = ld; g.strideM = strideM; g.batch = batch;
-    g.T = n / FGP_TILE; g.R = g.T + 1; g.nrows = n + 1;
+    g.T = n / FGP_TILE; g.n = n;
     g.W = W; g.strideW = strideW; g.info = info;
-    const size_t nL = (size_t)batch * g.R * g.T, nW = (size_t)batch * g.T;
-    g.flagL = (int*)flags; g.flagW = g.flagL + nL; g.counter = g.flagW + nW;
-    const long perMatrix = (long)g.T * g.R - (long)g.T * (g.T - 1) / 2;
+    const size_t nL = (size_t)batch * g.T * g.T, nW = (size_t)batch * g.T;
+    g.flagL = (int*)flags; g.flagW = g.flagL + nL; g.flagY = g.flagW + nW; g.counter = g.flagY + nW;
+    const long perMatrix = (long)g.T * (g.T + 1) / 2;
     if (perMatrix * batch > 0x7fffffffL / 2) return false;
     g.ntasks = (int)(perMatrix * batch);
     CUtensorMap mapM, mapW;
-    if (!make_map(&mapM, M, g.nrows, n, ld, batch, strideM)) return false;
+    if (!make_map(&mapM, M, n + 1, n, ld, batch, strideM)) return false;
     if (!make_map(&mapW, W, FGP_TILE, (long)g.T * FGP_TILE, FGP_TILE, batch, strideW)) return false;
     if (cudaMemsetAsync(flags, 0, chol_dag_flag_bytes(n, batch), st) != cudaSuccess) { cudaGetLastError(); return false; }
     const int sms = nsm[dev] > 0 ? nsm[dev] : 148;

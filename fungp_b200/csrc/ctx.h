@@ -114,8 +114,8 @@ struct fgp_ctx {
     int host_threads = 0;     // host threads of the chunked matrix transfers; 0 = min(16, cores)
     int out_prezeroed = 0;    // 1: the caller's L_out matrices are zero-filled on entry (calloc / numpy.zeros): only the lower triangle is written
     int host_thp = 1;         // ask for transparent huge pages on large host output matrices (model.cu copy_matrix)
-    int dag = 1;              // likelihood batches and preMats factor with the persistent dataflow kernel (chol_dag.cu) when n is a
-                              // multiple of 128; 2: the lock-step candidate driver too (measured slower there at n = 1024, faster from 2048)
+    int dag = 1;              // likelihood batches, preMats and the lock-step candidate driver factor with the persistent dataflow
+                              // kernel (chol_dag.cu) when n is a multiple of 128; 0: always the launch-per-step engine (chol.cu)
     int gemm_flat = 8;        // TMA kernel: persistent CTAs over all (tile, element) pairs from this many pairs per SM on (0 = never)
     int pdl = 1;              // programmatic dependent launch along the factorisation's kernel chain
     int fused_assembly = 1;   // batched likelihood calls assemble the matrices of one structure with the batch-fused kernel

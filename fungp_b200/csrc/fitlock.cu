@@ -567,7 +567,7 @@ struct Driver {
         }
         // ---- factorisations: groups of slots on the lane's streams (one group below n = 2048)
         // (dataflow Cholesky: all slots of the round in one persistent launch on the lane's first stream)
-        const bool useDag = B > 0 && (wc->dag >= 2 || (wc->dag == 1 && n >= 2048)) && !wc->profile && chol_dag_supported(n, n + 1) && !ln.dag.ensure(chol_dag_flag_bytes(n, B));
+        const bool useDag = B > 0 && wc->dag && !wc->profile && chol_dag_supported(n, n + 1) && !ln.dag.ensure(chol_dag_flag_bytes(n, B));
         const int ns = B > 0 ? (useDag ? 1 : std::max(1, std::min(nst, B))) : 0;
         if (ns > 1) LCK(cudaEventRecord(ln.evFork, s0));
         const int per = ns ? cdiv(B, ns) : 0;
