@@ -218,6 +218,7 @@ def run_ours(args):
     ctx.set_option("graphs", args.graphs)
     ctx.set_option("fit_mode", args.fit_mode)
     ctx.set_option("pdl", args.pdl)
+    ctx.set_option("dag", args.dag)
     ctx.set_option("fused_assembly", args.fused)
     if args.fit_lanes > 0:
         ctx.set_option("fit_lanes", args.fit_lanes)
@@ -268,8 +269,10 @@ def run_ours(args):
     l0 = ctx.launch_count()
     ctx.mark(0)
     t0 = time.perf_counter()
+    dag_ms = []                                   # device time of each step's dataflow-Cholesky launch (events on its stream)
     for _ in range(args.steps):
         nll_last = step_resident()
+        dag_ms.append(ctx.last_factor_ms())
     ctx.mark(1)
     barrier()
     wall = time.perf_counter() - t0
@@ -386,19 +389,55 @@ def run_ours(args):
         except Exception:
             hbm_peak = 6650.0
         traffic, traffic_note = None, None
-        for name in ("r02_traffic.json", "r01_traffic.json"):
+        dag_on = bool(dag_ms) and min(dag_ms) > 0
+        for name in (("r02_traffic_dag.json",) if dag_on else ()) + ("r02_traffic.json", "r01_traffic.json"):
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", name)))
-                traffic = tj["update_kernel_dram_bytes_per_launch"]
-                traffic_note = ("%s: ncu capture of the K=%d top-level update launch: %.1f GFLOP, %.1f MB algorithmic, %.1f TFLOP/s and "
-                                "DMMA pipe %.1f %% active under ncu" % (name, tj.get("K", 2048), tj["flops_per_launch"] / 1e9,
-                                                                        tj["algorithmic_bytes_per_launch"] / 1e6, tj["tflops_under_ncu"],
-                                                                        tj["dmma_pipe_active_pct"]))
+                if name == "r02_traffic_dag.json":
+                    traffic = tj["dram_bytes_per_launch"]
+                    traffic_note = ("%s: ncu --set full capture of one chol_dag_kernel launch of this workload (13 matrices): %.2f GB read + "
+                                    "%.2f GB written, algorithmic %.2f GB, %.1f TFLOP/s and DMMA pipe %.1f %% active under ncu"
+                                    % (name, tj["dram_bytes_read"] / 1e9, tj["dram_bytes_write"] / 1e9, tj["algorithmic_bytes_per_launch"] / 1e9,
+                                       tj["tflops_under_ncu"], tj["dmma_pipe_active_pct"]))
+                else:
+                    traffic = tj["update_kernel_dram_bytes_per_launch"]
+                    traffic_note = ("%s: ncu capture of the K=%d top-level update launch of the launch-per-step engine: %.1f GFLOP, %.1f MB "
+                                    "algorithmic, %.1f TFLOP/s and DMMA pipe %.1f %% active under ncu"
+                                    % (name, tj.get("K", 2048), tj["flops_per_launch"] / 1e9, tj["algorithmic_bytes_per_launch"] / 1e6,
+                                       tj["tflops_under_ncu"], tj["dmma_pipe_active_pct"]))
                 break
             except Exception:
                 pass
         chol_flops = n ** 3 / 3.0
         step_tf = chol_flops * total_evals / wall / world / 1e12      # per GPU, whole step, everything else included in the time
+        dag_avg = float(np.mean(dag_ms)) if dag_ms and min(dag_ms) > 0 else None
+        if dag_avg:
+            # the dominant kernel is ONE launch per step: chol_dag_kernel factors the step's 13 matrices (tile tasks: left-looking
+            # DMMA accumulation through the TMA ring + the diagonal-block / triangular-solve epilogues)
+            kern_tf = chol_flops * B / (dag_avg * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "chol_dag_kernel (the whole blocked Cholesky of the step's 13 matrices as one persistent "
+                                                     "kernel: FP64 DMMA m8n8k4, operands by TMA, tile-ready flags between CTAs)",
+                        "achieved": kern_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": kern_tf / fp64_peak,
+                        "launch_ms_avg": dag_avg, "launches_timed": len(dag_ms),
+                        "flops_per_launch": chol_flops * B,
+                        "note": "algorithmic flops (13 n^3/3) over the kernel's own duration, CUDA events on its stream inside the timed region",
+                        "whole_step": {"achieved": step_tf, "frac": step_tf / fp64_peak,
+                                       "note": "the same flops over the whole timed step (assembly, reductions, copies, host included)"},
+                        "traffic": traffic, "traffic_note": traffic_note,
+                        "peak_source": peak_src + "; MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = 37.2 TFLOP/s at 1965 MHz"}
+        else:
+            roofline = {"bound": "tensor", "kernel": "gemm_dmma_tma_kernel (trailing update of the blocked Cholesky: FP64 DMMA m8n8k4, "
+                                                     "operands by TMA) -- measured as the whole timed step",
+                        "achieved": step_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": step_tf / fp64_peak,
+                        "flops_per_step_per_gpu": chol_flops * B,
+                        "traffic": traffic, "traffic_note": traffic_note,
+                        "peak_source": peak_src + "; MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = 37.2 TFLOP/s at 1965 MHz"}
+        roofline["update_kernel_profiled"] = {
+            "note": "launch-per-step engine (option dag 0, profile mode): per-launch CUDA events, the step's 13 points as one batch on ONE stream; "
+                    "flops count the triangle of diagonal tiles",
+            "tflops": upd_tf, "frac": upd_tf / fp64_peak,
+            "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
+            "launch_ms_avg": tm["update_ms"] / max(1, tm["update_launches"])}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -416,27 +455,16 @@ def run_ours(args):
             "clocks": clocks,
             # achieved = ALGORITHMIC flops of the blocked Cholesky (n^3/3 per evaluation) over the timed step itself: assembly,
             # diagonal blocks, panel solves and reductions are all inside the time, so this can only understate the kernel
-            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_tma_kernel (trailing update of the blocked Cholesky: FP64 DMMA m8n8k4, "
-                                                      "operands by TMA) -- measured as the whole timed step",
-                         "achieved": step_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": step_tf / fp64_peak,
-                         "flops_per_step_per_gpu": chol_flops * B,
-                         "traffic": traffic, "traffic_note": traffic_note,
-                         "peak_source": peak_src + "; MEASURED_PEAKS.json has no FP64 entry; nominal B200 FP64 = 37.2 TFLOP/s "
-                                        "at 1965 MHz",
-                         "update_kernel_profiled": {"note": "per-launch CUDA events, the step's 13 points as one batch on ONE stream (the timed step "
-                                                            "spreads them over 8); flops count the triangle of diagonal tiles",
-                                                    "tflops": upd_tf, "frac": upd_tf / fp64_peak,
-                                                    "flops_per_launch_avg": tm["update_flops"] / max(1, tm["update_launches"]),
-                                                    "launch_ms_avg": tm["update_ms"] / max(1, tm["update_launches"])}},
+            "roofline": roofline,
             "single_eval": {"ms": single_ms, "tflops": chol_flops / (single_ms * 1e-3) / 1e12, "frac": chol_flops / (single_ms * 1e-3) / 1e12 / fp64_peak,
-                            "note": "one fgp_nll_batch call with B = 1 (look-ahead schedule), host wall clock, mean of 5"},
+                            "note": "one fgp_nll_batch call with B = 1, host wall clock, mean of 5"},
             "roofline_assembly": {"bound": "hbm", "kernel": "assemble_fused_kernel<gauss> (distance + correlation, lower triangles of the "
                                                             "step's 13 matrices in one launch)",
                                   "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                                   "algorithmic_bytes_per_launch": asm_bytes, "launch_ms": tm["assembly_ms"],
                                   "bytes_per_matrix": asm_bytes / B, "ms_per_matrix": tm["assembly_ms"] / B,
                                   "note": "FP64-issue bound: DMMA and DFMA share one datapath (DESIGN.md 2.3)"},
-            "kernel_ms_profiled_13evals_1stream": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
+            "kernel_ms_profiled_13evals_1stream_launch_per_step_engine": {k: tm[k] for k in ("assembly_ms", "factor_ms", "update_ms", "potf2_ms", "trsm_ms")},
             "fp64_peaks_measured": peaks,
             "nll_check": float(nll_last[0]),
         }
@@ -576,6 +604,7 @@ def main():
     ap.add_argument("--factory-cands", type=int, default=FACTORY["n_cand"],
                     help="length of the fixed candidate list for the factory metric, sharded over the GPUs (0 = skip)")
     ap.add_argument("--fit-mode", type=int, default=1, help="fgp_fit_batch: 1 lock-step driver (one host thread per GPU), 0 one thread per candidate")
+    ap.add_argument("--dag", type=int, default=1, help="dataflow Cholesky: one persistent kernel per likelihood batch (0 = launch-per-step engine)")
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch along the factorisation chain (0/1)")
     ap.add_argument("--fused", type=int, default=1, help="batch-fused assembly kernel (0/1)")
     ap.add_argument("--fit-lanes", type=int, default=0, help="lock-step rounds in flight per GPU (0 = library default)")

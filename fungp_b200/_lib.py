@@ -51,6 +51,7 @@ SIGNATURES = {
     "fgp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "fgp_launch_count": (C.c_longlong, []),
     "fgp_work_count": (C.c_longlong, [C.c_int]),
+    "fgp_last_factor_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "fgp_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "fgp_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "fgp_measure_peaks": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),

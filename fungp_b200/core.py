@@ -91,6 +91,12 @@ class Context:
         return dict(assembly_ms=out[0], factor_ms=out[1], update_ms=out[2], update_launches=int(out[3]),
                     update_flops=out[4], potf2_ms=out[5], trsm_ms=out[6], launches=int(out[7]))
 
+    def last_factor_ms(self):
+        """device time of the dataflow-Cholesky launch of the last nll_batch call (0.0 if it ran launch by launch)"""
+        ms = C.c_double()
+        self.check(self.lib.fgp_last_factor_ms(self.h, C.byref(ms)), "fgp_last_factor_ms")
+        return ms.value
+
     def launch_count(self):
         return int(self.lib.fgp_launch_count())
 

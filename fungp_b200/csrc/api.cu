@@ -120,6 +120,7 @@ extern "C" void fgp_ctx_destroy(fgp_ctx* ctx) {
         if (d.evA) cudaEventDestroy(d.evA);
         if (d.evB) cudaEventDestroy(d.evB);
         if (d.evWait) cudaEventDestroy(d.evWait);
+        for (int e = 0; e < 2; ++e) if (d.evDag[e]) cudaEventDestroy(d.evDag[e]);
         d.work.release(); d.wbuf.release(); d.small.release(); d.aux.release(); d.dagFlags.release(); d.pool.release();
         if (d.pinned) cudaFreeHost(d.pinned);
     }
@@ -172,6 +173,18 @@ extern "C" int fgp_get_timing(fgp_ctx* ctx, double* out8) {
     out8[5] = ms[FgpTimers::PANEL];
     out8[6] = ms[FgpTimers::TRSM];
     out8[7] = cnt[FgpTimers::UPDATE] + cnt[FgpTimers::PANEL] + cnt[FgpTimers::TRSM] + cnt[FgpTimers::ASSEMBLY];
+    return 0;
+}
+
+extern "C" int fgp_last_factor_ms(fgp_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return FGP_ERR_ARG;
+    DevState& d = ctx->dev[0];
+    *ms = 0.0;
+    if (!d.dagTimed || !d.evDag[0] || !d.evDag[1]) return 0;
+    CK(cudaSetDevice(d.device));
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, d.evDag[0], d.evDag[1]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    *ms = f;
     return 0;
 }
 
@@ -602,7 +615,17 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             t.info = dInfo + g0;
             if (prof) d.timers.begin(st);
             cudaEvent_t fa = prof ? d.timers.cur : nullptr;
-            if (!(useDag && launch_chol_dag(t.M, t.ld, t.strideM, gb, n, t.W, t.strideW, t.info, d.dagFlags.p, st))) {
+            bool dagDone = false;
+            if (useDag) {
+                // timed with two events on its own stream (one launch: the price is two event records per call)
+                for (int e = 0; e < 2; ++e)
+                    if (!d.evDag[e]) CK(cudaEventCreate(&d.evDag[e]));
+                CK(cudaEventRecord(d.evDag[0], st));
+                dagDone = launch_chol_dag(t.M, t.ld, t.strideM, gb, n, t.W, t.strideW, t.info, d.dagFlags.p, st);
+                CK(cudaEventRecord(d.evDag[1], st));
+                d.dagTimed = dagDone;
+            }
+            if (!dagDone) {
                 const int rcf = trap_factor(ctx, slot, t, st, d.sBulk, ctx->lookahead && ns == 1 && gb == 1);
                 if (rcf) return rcf;
             }

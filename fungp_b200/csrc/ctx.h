@@ -90,6 +90,8 @@ struct DevState {
     cudaStream_t sBulk = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr, evJoin[MAXSTREAMS] = {nullptr}, evMark[4] = {nullptr};
     cudaEvent_t evWait = nullptr;   // blocking-sync event of wait_stream (fit_batch workers)
+    cudaEvent_t evDag[2] = {nullptr, nullptr};   // around the last dataflow-Cholesky launch of fgp_nll_batch (fgp_last_factor_ms)
+    bool dagTimed = false;
     DevBuf work;      // factorisation workspaces (batch of trapezoids)
     DevBuf wbuf;      // inverse diagonal blocks
     DevBuf small;     // thetas / scales / results
