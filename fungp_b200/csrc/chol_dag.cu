@@ -55,6 +55,7 @@ static_assert(potf2::LDT == PITCH, "one layout for the hand-over tile, potf2's T
 struct DagArgs {
     double* M; long ld; long strideM;
     int batch, T, n;               // T = n / 128 tile rows and columns; the y row (row n) rides along in the diagonal tasks
+    int G;                         // tile columns per claim group (divides T)
     double* W; long strideW;
     int* info;
     int* flagL;                    // [batch][T][T]  L(i,j) stored
@@ -188,15 +189,30 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
     int gc = 0;   // chunks this CTA has sent through the ring so far (ring position and barrier phases)
     int task = sTask[0];
     for (int it = 0; task < g.ntasks; ++it) {
-        // column j holds B (T - j) tasks -- the B diagonal tiles, then row by row; before column j: B (j T - j (j - 1) / 2)
-        const int q = task / B;
-        int j = (int)(((float)(2 * T + 1) - sqrtf((float)(2 * T + 1) * (float)(2 * T + 1) - 8.0f * (float)q)) * 0.5f);
-        j = max(0, min(j, T - 1));
-        while (j + 1 < T && (j + 1) * T - (j + 1) * j / 2 <= q) ++j;
-        while (j > 0 && j * T - j * (j - 1) / 2 > q) --j;
-        const int local = task - B * (j * T - j * (j - 1) / 2);
-        const int i = j + local / B;
-        const int b = local - (local / B) * B;
+        // Claim order: groups of G tile columns; inside a group row by row, inside a row matrix by matrix, and for each
+        // the (up to G) tiles of the row.  G = 1 is plain column order.  With G > 1 the tiles (i, j), (i, j+1), ... of one
+        // row run side by side on neighbouring CTAs and stream the same L(i, :) chunks at the same time (one HBM read,
+        // G - 1 L2 hits), at the price of a short wait at their ends (tile (i, j+1) needs L(i, j)).
+        const int G = g.G;
+        int qg = 0;
+        long pre = 0;
+        for (;;) {
+            const long cnt = (long)B * (G * (G + 1) / 2 + (T - (qg + 1) * G) * G);
+            if ((long)task < pre + cnt) break;
+            pre += cnt; ++qg;
+        }
+        int local = (int)((long)task - pre);
+        const int j0 = qg * G;
+        int i, j, b;
+        int rr = 0;
+        while (rr < G && local >= B * (rr + 1)) { local -= B * (rr + 1); ++rr; }
+        if (rr < G) { i = j0 + rr; b = local / (rr + 1); j = j0 + local - b * (rr + 1); }
+        else {
+            const int per = B * G;
+            i = j0 + G + local / per;
+            const int l2 = local - (local / per) * per;
+            b = l2 / G; j = j0 + l2 - b * G;
+        }
         const bool diag = i == j;
         const int rowBase = i * FGP_TILE, colBase = j * FGP_TILE;
         double* C = g.M + (long)b * g.strideM;
@@ -424,7 +440,7 @@ size_t chol_dag_flag_bytes(int n, int batch) {
 // receives the inverse diagonal blocks, info the failing minor orders.  flags: chol_dag_flag_bytes() of device memory.
 // Returns false when the launch cannot be taken (driver entry point missing, alignment) -- the caller then runs chol.cu.
 bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
-                     cudaStream_t st) {
+                     cudaStream_t st, int group) {
     static bool attr_set[FGP_MAXDEV] = {false};
     static int nsm[FGP_MAXDEV] = {0};
     if (!chol_dag_supported(n, n + 1) || batch <= 0) return false;
@@ -452,6 +468,7 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
     DagArgs g{};
     g.M = M; g.ld = ld; g.strideM = strideM; g.batch = batch;
     g.T = n / FGP_TILE; g.n = n;
+    g.G = (group > 1 && g.T % group == 0) ? group : 1;
     g.W = W; g.strideW = strideW; g.info = info;
     const size_t nL = (size_t)batch * g.T * g.T, nW = (size_t)batch * g.T;
     g.flagL = (int*)flags; g.flagW = g.flagL + nL; g.flagY = g.flagW + nW; g.counter = g.flagY + nW;
