@@ -24,8 +24,9 @@
 // updates also accumulate k ascending, merely interrupted by exact stores and loads; one FP64 DMMA m8n8k4 is four
 // chained FMAs in k order, tools/dmma_order.cu), the same potf2 code; only products with exact zeros of W_j are left
 // out: results are bit-identical (tests/test_gpu_parity.py::test_dataflow_cholesky_is_bit_identical).
-// Scope: n a multiple of 128 (all tiles full, the y row is row n), no holes, nothing prefactored; everything else
-// (ragged n, predict / simulate / LOOCV / update trapezoids) stays on chol.cu.
+// Scope: the plain (n + 1)-row trapezoid -- any n; rows and columns from n on are masked in the last tile row / column and
+// the last diagonal block is padded with the identity as in potf2_inv_kernel -- no holes, nothing prefactored: predict /
+// simulate / LOOCV / update trapezoids stay on chol.cu.
 #include "potf2_body.cuh"
 #include <cuda.h>
 #include <algorithm>
@@ -126,14 +127,14 @@ __device__ __forceinline__ void wait_flag(const int* p) {
 // solve of the launch-per-step engine performs (one m8n8k4 DMMA IS four chained FMAs in k order, tools/dmma_order.cu) --
 // then L(j,j).  Not inlined: the block algorithm runs at 255 registers on its own and must not share an allocation with
 // the 128 accumulator registers of the tile loop.
-__device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* infoPtr, int infoOff, double* Mdiag, long ld, double* Wb,
+__device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* infoPtr, int infoOff, double* Mdiag, long ld, int nb, double* Wb,
                                            int* flagW, const double* ay, double* yOut, int* flagY) {
     potf2::factor_block(smem, pbar, infoPtr, infoOff);
     potf2::store_W(smem, Wb);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release(flagW, 1);
-    if (threadIdx.x < FGP_TILE) {
+    if (threadIdx.x < nb) {
         const int c = threadIdx.x;
         const double* Tc = smem + c * potf2::LDT;                 // strict upper part of column c: E(k, c) = W(c, k), k < c
         const double* dinvE = smem + potf2::NB * potf2::LDT + potf2::SB * potf2::XLD + potf2::SB * potf2::ELD;
@@ -145,7 +146,7 @@ __device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* inf
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release(flagY, 1);
-    potf2::store_L(smem, Mdiag, ld, FGP_TILE);
+    potf2::store_L(smem, Mdiag, ld, nb);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -237,9 +238,12 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         const int ycol = (wm == 0 ? 0 : 64) + lane;
         const double* yrow = C + g.n;                                    // element k of the y row: yrow[k * ld]
         double ay0 = 0.0, ay1 = 0.0;
+        // ragged last tile row / column (n not a multiple of 128): rows and columns from n on do not exist
+        const int nbRows = min(FGP_TILE, g.n - rowBase), nbCols = min(FGP_TILE, g.n - colBase);
+        const bool fullTile = nbRows == FGP_TILE && nbCols == FGP_TILE;
         if (ywarp) {
-            ay0 = __ldcg(yrow + (long)(colBase + ycol) * g.ld);
-            ay1 = __ldcg(yrow + (long)(colBase + ycol + 32) * g.ld);
+            if (ycol < nbCols) ay0 = __ldcg(yrow + (long)(colBase + ycol) * g.ld);
+            if (ycol + 32 < nbCols) ay1 = __ldcg(yrow + (long)(colBase + ycol + 32) * g.ld);
         }
         double* Cw = C + (long)(rowBase + wm * 32 + r_lane) + (long)(colBase + wn * 64 + c_lane) * g.ld;
 
@@ -265,7 +269,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         }
 
         double acc[4][8][2];
-        if (active) {
+        if (active && fullTile) {
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
@@ -278,6 +282,17 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+            if (active) {
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) {
+                        const bool rok = wm * 32 + mi * 8 + r_lane < nbRows;
+                        const int cl = wn * 64 + ni * 8 + c_lane;
+                        if (rok && cl < nbCols) acc[mi][ni][0] = Cw[mi * 8 + (long)(ni * 8) * g.ld];
+                        if (rok && cl + 1 < nbCols) acc[mi][ni][1] = Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld];
+                    }
+            }
         }
 
         // ---- acc -= L(i, 0:j) L(j, 0:j)'
@@ -339,13 +354,19 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = wm * 32 + mi * 8 + r_lane, c = wn * 64 + ni * 8 + c_lane + h;
-                    smem[c * PITCH + r] = (diag && r < c) ? 0.0 : acc[mi][ni][h];
+                    double v = acc[mi][ni][h];
+                    if (diag) {
+                        // potf2's input: the lower triangle of the nb x nb block, identity padding, zeros above the diagonal
+                        if (r < c) v = 0.0;
+                        else if (r >= nbRows || c >= nbCols) v = (r == c) ? 1.0 : 0.0;
+                    }
+                    smem[c * PITCH + r] = v;
                 }
 
         if (diag) {
-            if (ywarp) { ay[ycol] = ay0; ay[ycol + 32] = ay1; }
+            if (ywarp) { ay[ycol] = ycol < nbCols ? ay0 : 0.0; ay[ycol + 32] = ycol + 32 < nbCols ? ay1 : 0.0; }
             __syncthreads();
-            diag_epilogue(smem, pbar, g.info ? g.info + b : nullptr, colBase, C + (long)colBase + (long)colBase * g.ld, g.ld,
+            diag_epilogue(smem, pbar, g.info ? g.info + b : nullptr, colBase, C + (long)colBase + (long)colBase * g.ld, g.ld, nbCols,
                           g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE, g.flagW + (long)b * T + j, ay,
                           C + g.n + (long)colBase * g.ld, g.flagY + (long)b * T + j);
             __syncthreads();     // the hand-over area is free again
@@ -394,13 +415,24 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                     tma_load_3d(wslab + (uint32_t)((cw & 1) * OPER * 8), &mapW, wfullB + 8 * (cw & 1), 0, j * FGP_TILE + (cw + 2) * KC, b);
                 }
             }
+            if (fullTile) {
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni)
+                for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
-                    Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
-                    Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
-                }
+                    for (int mi = 0; mi < 4; ++mi) {
+                        Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
+                        Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
+                    }
+            } else {         // last tile row: rows from n on do not exist (off-diagonal tiles always have all 128 columns)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+                        if (wm * 32 + mi * 8 + r_lane < nbRows) {
+                            Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
+                            Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
+                        }
+            }
             __threadfence();
             __syncthreads();
             if (producer) st_release(g.flagL + ((long)b * T + i) * T + j, 1);
@@ -429,10 +461,10 @@ bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, lo
 
 }  // namespace
 
-bool chol_dag_supported(int n, int nrows) { return n > 0 && n % FGP_TILE == 0 && nrows == n + 1; }
+bool chol_dag_supported(int n, int nrows) { return n > 0 && nrows == n + 1; }
 
 size_t chol_dag_flag_bytes(int n, int batch) {
-    const size_t T = (size_t)n / FGP_TILE;
+    const size_t T = ((size_t)n + FGP_TILE - 1) / FGP_TILE;
     return sizeof(int) * ((size_t)batch * T * T + 2 * (size_t)batch * T + 4);
 }
 
@@ -467,7 +499,7 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
     }
     DagArgs g{};
     g.M = M; g.ld = ld; g.strideM = strideM; g.batch = batch;
-    g.T = n / FGP_TILE; g.n = n;
+    g.T = (n + FGP_TILE - 1) / FGP_TILE; g.n = n;
     g.G = (group > 1 && g.T % group == 0) ? group : 1;
     g.W = W; g.strideW = strideW; g.info = info;
     const size_t nL = (size_t)batch * g.T * g.T, nW = (size_t)batch * g.T;
@@ -477,7 +509,7 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
     g.ntasks = (int)(perMatrix * batch);
     CUtensorMap mapM, mapW;
     if (!make_map(&mapM, M, n + 1, n, ld, batch, strideM)) return false;
-    if (!make_map(&mapW, W, FGP_TILE, (long)g.T * FGP_TILE, FGP_TILE, batch, strideW)) return false;
+    if (!make_map(&mapW, W, FGP_TILE, (long)g.T * FGP_TILE, FGP_TILE, batch, strideW)) return false;      // W_j unit-padded: always 128 x 128
     if (cudaMemsetAsync(flags, 0, chol_dag_flag_bytes(n, batch), st) != cudaSuccess) { cudaGetLastError(); return false; }
     const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
     FGP_COUNT_LAUNCH();

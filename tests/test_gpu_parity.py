@@ -728,11 +728,12 @@ def test_tma_and_cp_async_gemm_kernels_agree_bitwise(ctx):
     P.close()
 
 
-@pytest.mark.parametrize("n,B", [(128, 1), (384, 4), (1024, 7), (2560, 3)])
+@pytest.mark.parametrize("n,B", [(128, 1), (384, 4), (1024, 7), (2560, 3), (57, 2), (129, 1), (333, 3), (1407, 4)])
 def test_dataflow_cholesky_is_bit_identical(ctx, n, B):
     """csrc/chol_dag.cu -- the factorisation of a whole batch as one persistent kernel of tile tasks (left-looking
     accumulation through the TMA ring, the diagonal block and the triangular solve as epilogues, ready flags between
-    CTAs) -- against the launch-per-step engine of csrc/chol.cu: the same DMMA sequence per entry, so likelihoods, the
+    CTAs; ragged n: masked last tile row / column, identity-padded last diagonal block) -- against the launch-per-step
+    engine of csrc/chol.cu: the same sequence of fused multiply-adds per entry, so likelihoods, the
     stored factor, L^-1 y and everything computed from them agree to the last bit; and against the oracle.  Also: a
     matrix that is not positive definite reports the same minor and does not stall the kernel."""
     seed, m = 300 + n, 40
