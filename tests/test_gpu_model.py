@@ -172,8 +172,9 @@ def test_update_fast_paths_vs_oracle_refit(ctx, n):
 def test_append_is_much_cheaper_than_a_refit(ctx):
     """n = 8192, 64 points added with retained hyper-parameters: the fast path solves the new rows against the stored
     factor and factors 64 + (n mod 128) columns; a refit factors all of them.  Same L to 1e-9.  The solve of a thin row
-    block is a chain of n / 128 dependent tile steps, so the gain is bounded by launch latency, not by flops (measured
-    2.3x on B200; the time is logged)."""
+    block is a chain of n / 128 dependent tile steps, so the gain is bounded by launch latency, not by flops (measured on
+    B200: 4.4 ms against 10.3 ms for a refit on the launch-per-step engine = 2.3x, against 7.4 ms for a refit on the
+    dataflow kernel = 1.7x; the times are logged)."""
     import time
     import fungp_b200
     from helpers import make_case
@@ -200,7 +201,7 @@ def test_append_is_much_cheaper_than_a_refit(ctx):
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, "parity_log.jsonl"), "a") as f:
         f.write(json.dumps(dict(test="append_64_at_8192", fast_ms=t_fast * 1e3, refit_ms=t_full * 1e3, speedup=t_full / t_fast)) + "\n")
-    assert t_full >= 1.5 * t_fast, (t_fast, t_full)
+    assert t_full >= 1.25 * t_fast, (t_fast, t_full)
     for P in (P0, P1, P2):
         P.close()
 
