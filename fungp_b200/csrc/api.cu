@@ -146,6 +146,7 @@ extern "C" int fgp_set_option(fgp_ctx* ctx, const char* name, double value) {
     else if (!strcmp(name, "out_prezeroed")) ctx->out_prezeroed = value != 0 ? 1 : 0;
     else if (!strcmp(name, "host_thp")) ctx->host_thp = value != 0 ? 1 : 0;
     else if (!strcmp(name, "dag")) ctx->dag = value != 0 ? 1 : 0;
+    else if (!strcmp(name, "dag_order")) ctx->dag_order = value != 0 ? 1 : 0;
     else if (!strcmp(name, "dag_group")) ctx->dag_group = std::max(1, std::min((int)value, 16));
     else if (!strcmp(name, "gemm_flat")) ctx->gemm_flat = value < 0 ? 0 : (int)value;
     else if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value != 0 ? 1 : 0; g_plain_tma = ctx->gemm_tma; }
@@ -622,7 +623,7 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
                 for (int e = 0; e < 2; ++e)
                     if (!d.evDag[e]) CK(cudaEventCreate(&d.evDag[e]));
                 CK(cudaEventRecord(d.evDag[0], st));
-                dagDone = launch_chol_dag(t.M, t.ld, t.strideM, gb, n, t.W, t.strideW, t.info, d.dagFlags.p, st, ctx->dag_group);
+                dagDone = launch_chol_dag(t.M, t.ld, t.strideM, gb, n, t.W, t.strideW, t.info, d.dagFlags.p, st, ctx->dag_group, ctx->dag_order);
                 CK(cudaEventRecord(d.evDag[1], st));
                 d.dagTimed = dagDone;
             }

@@ -57,6 +57,7 @@ struct DagArgs {
     double* M; long ld; long strideM;
     int batch, T, n;               // T = n / 128 tile rows and columns; the y row (row n) rides along in the diagonal tasks
     int G;                         // tile columns per claim group (divides T)
+    int matrixMajor;               // claim order below the diagonal tiles of a group: 1 = matrix, row; 0 = row, matrix
     double* W; long strideW;
     int* info;
     int* flagL;                    // [batch][T][T]  L(i,j) stored
@@ -208,7 +209,14 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         int rr = 0;
         while (rr < G && local >= B * (rr + 1)) { local -= B * (rr + 1); ++rr; }
         if (rr < G) { i = j0 + rr; b = local / (rr + 1); j = j0 + local - b * (rr + 1); }
-        else {
+        else if (g.matrixMajor) {
+            // below the group's triangle: matrix by matrix, inside a matrix row by row -- tiles that read the same L(j, :)
+            // are claimed back to back, start within microseconds of each other and share its chunks in L2
+            const int perB = (T - j0 - G) * G;
+            b = local / perB;
+            const int l2 = local - b * perB;
+            i = j0 + G + l2 / G; j = j0 + l2 - (l2 / G) * G;
+        } else {
             const int per = B * G;
             i = j0 + G + local / per;
             const int l2 = local - (local / per) * per;
@@ -472,7 +480,7 @@ size_t chol_dag_flag_bytes(int n, int batch) {
 // receives the inverse diagonal blocks, info the failing minor orders.  flags: chol_dag_flag_bytes() of device memory.
 // Returns false when the launch cannot be taken (driver entry point missing, alignment) -- the caller then runs chol.cu.
 bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
-                     cudaStream_t st, int group) {
+                     cudaStream_t st, int group, int matrixMajor) {
     static bool attr_set[FGP_MAXDEV] = {false};
     static int nsm[FGP_MAXDEV] = {0};
     if (!chol_dag_supported(n, n + 1) || batch <= 0) return false;
@@ -501,6 +509,7 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
     g.M = M; g.ld = ld; g.strideM = strideM; g.batch = batch;
     g.T = (n + FGP_TILE - 1) / FGP_TILE; g.n = n;
     g.G = (group > 1 && g.T % group == 0) ? group : 1;
+    g.matrixMajor = matrixMajor;
     g.W = W; g.strideW = strideW; g.info = info;
     const size_t nL = (size_t)batch * g.T * g.T, nW = (size_t)batch * g.T;
     g.flagL = (int*)flags; g.flagW = g.flagL + nL; g.flagY = g.flagW + nW; g.counter = g.flagY + nW;

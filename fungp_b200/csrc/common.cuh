@@ -115,7 +115,7 @@ void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, d
 bool chol_dag_supported(int n, int nrows);
 size_t chol_dag_flag_bytes(int n, int batch);
 bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
-                     cudaStream_t st, int group = 1);
+                     cudaStream_t st, int group = 1, int matrixMajor = 1);
 
 struct GemmArgs {
     const double* A; long lda; long strideA;   // row operand: element (r, kk) = A[r + kk*lda], r = global row

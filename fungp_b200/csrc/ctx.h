@@ -116,6 +116,7 @@ struct fgp_ctx {
     int host_threads = 0;     // host threads of the chunked matrix transfers; 0 = min(16, cores)
     int out_prezeroed = 0;    // 1: the caller's L_out matrices are zero-filled on entry (calloc / numpy.zeros): only the lower triangle is written
     int host_thp = 1;         // ask for transparent huge pages on large host output matrices (model.cu copy_matrix)
+    int dag_order = 1;        // dataflow Cholesky: 1 = tiles of a column claimed matrix by matrix, 0 = row by row over the matrices
     int dag_group = 1;        // dataflow Cholesky: tile columns claimed together (1, 2, 4; see chol_dag.cu)
     int dag = 1;              // likelihood batches, preMats and the lock-step candidate driver factor with the persistent dataflow
                               // kernel (chol_dag.cu) when n is a multiple of 128; 0: always the launch-per-step engine (chol.cu)

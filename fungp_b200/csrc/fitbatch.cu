@@ -215,7 +215,7 @@ static int fit_batch_impl(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
                 fgp_ctx* wc = *slot;
                 cudaSetDevice(device);
                 wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
-                wc->blockingSync = blocking; wc->graphs = ctx->graphs; wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat; wc->dag = ctx->dag;
+                wc->blockingSync = blocking; wc->graphs = ctx->graphs; wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat; wc->dag = ctx->dag; wc->dag_order = ctx->dag_order;
                 for (;;) {
                     const int q = S.next.fetch_add(1);
                     if (q >= n_items) break;

@@ -583,7 +583,7 @@ struct Driver {
             t.ncols = n; t.nrows = n + 1; t.holeLo = n + 1; t.holeHi = n + 1; t.colHoleLo = n; t.colHoleHi = n; t.cpre = 0; t.upperRows = 0;
             t.W = (double*)ln.wbuf.p + (size_t)g0 * ncT * FGP_TILE * FGP_TILE; t.strideW = (long)ncT * FGP_TILE * FGP_TILE;
             t.info = dInfo + g0;
-            if (!(useDag && launch_chol_dag(t.M, t.ld, t.strideM, t.batch, n, t.W, t.strideW, t.info, ln.dag.p, st))) {
+            if (!(useDag && launch_chol_dag(t.M, t.ld, t.strideM, t.batch, n, t.W, t.strideW, t.info, ln.dag.p, st, 1, wc->dag_order))) {
                 int rc = trap_factor(wc, 0, t, st, nullptr, false);
                 if (rc) return rc;
             }
@@ -735,7 +735,7 @@ int fit_lockstep(fgp_ctx* ctx, Shared& S, const std::vector<int>& order) {
             cudaSetDevice(device);
             wc->streams = ctx->streams; wc->outer = ctx->outer; wc->outer_single = ctx->outer_single; wc->lookahead = ctx->lookahead;
             wc->fit_points = ctx->fit_points; wc->fit_lanes = ctx->fit_lanes; wc->predict_reserve = ctx->predict_reserve;
-            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat; wc->dag = ctx->dag;
+            wc->fused_assembly = ctx->fused_assembly; wc->pdl = ctx->pdl; wc->gemm_tma = ctx->gemm_tma; wc->gemm_flat = ctx->gemm_flat; wc->dag = ctx->dag; wc->dag_order = ctx->dag_order;
             wc->blockingSync = ctx->fit_blocking > 0 ? ctx->fit_blocking : 0;
             // option "profile": per-launch CUDA events of this call's rounds on the first GPU (meaningful with fit_lanes = 1,
             // where the rounds do not overlap); fgp_get_timing on the caller's context reports them

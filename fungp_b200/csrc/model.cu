@@ -242,7 +242,7 @@ extern "C" int fgp_premats(fgp_problem* P, int ker, double nugget, double sig2, 
     t.ncols = n; t.nrows = n + 1; t.holeLo = n + 1; t.holeHi = n + 1; t.colHoleLo = n; t.colHoleHi = n;
     t.cpre = 0; t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
     if (!(ctx->dag && !ctx->profile && chol_dag_supported(n, n + 1) && !d.dagFlags.ensure(chol_dag_flag_bytes(n, 1)) &&
-          launch_chol_dag(t.M, t.ld, t.strideM, 1, n, t.W, t.strideW, t.info, d.dagFlags.p, st))) {
+          launch_chol_dag(t.M, t.ld, t.strideM, 1, n, t.W, t.strideW, t.info, d.dagFlags.p, st, 1, ctx->dag_order))) {
         rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
         if (rc) return rc;
     }

@@ -10,7 +10,9 @@ ctx = fungp_b200.Context(1)
 for a in sys.argv[1:]:
     if a.startswith("G"):
         ctx.set_option("dag_group", int(a[1:]))
-cases = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:] if not a.startswith("G")] or [(256, 1), (256, 3), (1024, 1), (1024, 60), (2048, 20), (8192, 1), (8192, 13)]
+    if a.startswith("O"):
+        ctx.set_option("dag_order", int(a[1:]))
+cases = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:] if not a.startswith(("G", "O"))] or [(256, 1), (256, 3), (1024, 1), (1024, 60), (2048, 20), (8192, 1), (8192, 13)]
 for n, B in cases:
     sIn, fIn, y = synth.make_data(n, n, 4, [100, 100])
     proj = [ctx.project(f, 5, "B-splines") for f in fIn]

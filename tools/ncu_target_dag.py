@@ -7,7 +7,8 @@ sys.path.insert(0, ROOT)
 import bench, fungp_b200
 from fungp_b200 import synth
 ctx = fungp_b200.Context(1)
-ctx.set_option("dag_group", int(os.environ.get("FGP_DAG_GROUP", "1")))      # claim-group experiment (tools/dag_group_exp.sh)
+ctx.set_option("dag_group", int(os.environ.get("FGP_DAG_GROUP", "1")))      # claim-order experiments
+ctx.set_option("dag_order", int(os.environ.get("FGP_DAG_ORDER", "1")))
 sIn, fIn, y = bench.build_inputs()
 C = bench.CFG
 proj = [ctx.project(f, p, C["basis"]) for f, p in zip(fIn, C["pdims"])]
