@@ -53,6 +53,15 @@ static_assert(potf2::POTF2_WORK_DOUBLES * 8 <= RING_BYTES, "potf2 works inside t
 static_assert(potf2::NB * potf2::LDT * 8 == 2 * STAGE * 8, "hand-over tile = stages 0 and 1");
 static_assert(potf2::LDT == PITCH, "one layout for the hand-over tile, potf2's T and the solve's A operand");
 
+#ifdef FGP_DAG_PROF
+// development aid: SM clocks per phase summed over all CTAs: [0] claim + decode + ready scan  [1] tile loop (incl. waits for
+// inputs)  [2] diagonal epilogue  [3] solve epilogue (incl. the wait for W_j)  [4] tasks  [5] diagonal tasks  [6] kernel
+__device__ unsigned long long g_dag_prof[16];      // [8] solve: hand-over + W wait  [9] solve: products  [10] solve: stores + fence
+#define DPROF(i, t0) do { if (threadIdx.x == 0) atomicAdd(&g_dag_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define DPROF(i, t0) do { } while (0)
+#endif
+
 struct DagArgs {
     double* M; long ld; long strideM;
     int batch, T, n;               // T = n / 128 tile rows and columns; the y row (row n) rides along in the diagonal tasks
@@ -190,7 +199,13 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 
     int gc = 0;   // chunks this CTA has sent through the ring so far (ring position and barrier phases)
     int task = sTask[0];
+#ifdef FGP_DAG_PROF
+    const long long tKernel = clock64();
+#endif
     for (int it = 0; task < g.ntasks; ++it) {
+#ifdef FGP_DAG_PROF
+        long long tPh = clock64();
+#endif
         // Claim order: groups of G tile columns; inside a group row by row, inside a row matrix by matrix, and for each
         // the (up to G) tiles of the row.  G = 1 is plain column order.  With G > 1 the tiles (i, j), (i, j+1), ... of one
         // row run side by side on neighbouring CTAs and stream the same L(i, :) chunks at the same time (one HBM read,
@@ -238,6 +253,10 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             else ready = ready && ld_acquire(fY + kt) != 0;
         }
         const bool allReady = __syncthreads_and(ready) != 0;
+#ifdef FGP_DAG_PROF
+        DPROF(0, tPh); tPh = clock64();
+        if (threadIdx.x == 0) { atomicAdd(&g_dag_prof[4], 1ULL); if (diag) atomicAdd(&g_dag_prof[5], 1ULL); }
+#endif
 
         // diagonal tiles: the two warps that lie entirely above the diagonal carry the y row instead -- 64 columns each,
         // two per lane: ay(c) -= sum_k y(k) L(j-tile row c, k), FMAs in k order on the B slabs that pass through the ring
@@ -352,6 +371,9 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             if (lane == 0) mbar_arrive(emptyB + 8 * s);
         }
         __syncthreads();     // every warp has left the ring
+#ifdef FGP_DAG_PROF
+        DPROF(1, tPh); tPh = clock64();
+#endif
         if (producer && claimAhead) sTask[(it + 1) & 1] = atomicAdd(g.counter, 1);
 
         // ---- hand the tile over in shared memory: [column][132 rows] -- potf2's T, and the solve's A operand ([k][row])
@@ -391,6 +413,10 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                 }
             }
             __syncthreads();     // hand-over tile complete
+#ifdef FGP_DAG_PROF
+            long long tS = clock64();
+            DPROF(8, tPh);
+#endif
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -423,6 +449,9 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                     tma_load_3d(wslab + (uint32_t)((cw & 1) * OPER * 8), &mapW, wfullB + 8 * (cw & 1), 0, j * FGP_TILE + (cw + 2) * KC, b);
                 }
             }
+#ifdef FGP_DAG_PROF
+            DPROF(9, tS); tS = clock64();
+#endif
             if (fullTile) {
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni)
@@ -443,12 +472,21 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             }
             __threadfence();
             __syncthreads();
+#ifdef FGP_DAG_PROF
+            DPROF(10, tS);
+#endif
             if (producer) st_release(g.flagL + ((long)b * T + i) * T + j, 1);
         }
         if (producer && !claimAhead) sTask[(it + 1) & 1] = atomicAdd(g.counter, 1);
         __syncthreads();
+#ifdef FGP_DAG_PROF
+        DPROF(diag ? 2 : 3, tPh);
+#endif
         task = sTask[(it + 1) & 1];
     }
+#ifdef FGP_DAG_PROF
+    DPROF(6, tKernel);
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -468,6 +506,13 @@ bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, lo
 }
 
 }  // namespace
+
+#ifdef FGP_DAG_PROF
+extern "C" void fgp_dag_prof_read(unsigned long long* out8, int reset) {
+    cudaMemcpyFromSymbol(out8, g_dag_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_dag_prof, z, sizeof(z)); }
+}
+#endif
 
 bool chol_dag_supported(int n, int nrows) { return n > 0 && nrows == n + 1; }
 
