@@ -436,12 +436,19 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                     for (int mi = 0; mi < 4; ++mi) a[mi] = As[kk * 4 * PITCH + mi * 8];
 #pragma unroll
                     for (int ni = 0; ni < 8; ++ni) bb[ni] = Bs[kk * 4 * PITCH + ni * 8];
+                    if (niSkip <= 0) {               // nothing to skip (most of the work): the plain unrolled block
 #pragma unroll
-                    for (int ni = 0; ni < 8; ++ni)
-                        if (ni >= niSkip) {
+                        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
-                        }
+                            for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                    } else {
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni)
+                            if (ni >= niSkip) {
+#pragma unroll
+                                for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bb[ni]);
+                            }
+                    }
                 }
                 __syncthreads();     // slab cw & 1 is free again
                 if (producer && cw + 2 < FGP_TILE / KC) {
