@@ -22,6 +22,7 @@ SIGNATURES = {
     "fgp_version": (C.c_char_p, []),
     "fgp_bspline_basis": (C.c_int, [C.c_int, C.c_int, c_dp]),
     "fgp_project": (C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]),
+    "fgp_test_dag_order": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_ip, c_ip]),
     "fgp_test_project_host": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     "fgp_problem_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dpp, c_dpp, c_dp,
                                      C.POINTER(C.c_void_p)]),

@@ -76,6 +76,42 @@ struct DagArgs {
     int ntasks;
 };
 
+// Claim order of the tile tasks: task number -> (tile row i, tile column j, matrix b).  Groups of G tile columns; inside
+// a group the G (G + 1) / 2 tiles of its triangle first (row by row, every matrix), then the tiles below -- matrix by
+// matrix and row by row inside a matrix (matrixMajor: tiles that read the same L(j, :) are claimed back to back, start
+// within microseconds of each other and share its chunks in L2), or row by row over the matrices.  G = 1 is plain
+// column order: a column's diagonal tiles of all matrices, then the rest.  With G > 1 the tiles (i, j), (i, j+1), ... of
+// one row run side by side on neighbouring CTAs and stream the same L(i, :) chunks at the same time, at the price of a
+// short wait at their ends (tile (i, j+1) needs L(i, j)).  Whatever the parameters, every input of a task -- L(i, k) and
+// L(j, k) for k < j, W_j, for diagonal tiles the y entries of the columns before -- belongs to a task with a SMALLER
+// number: that is what makes the spin-waits of the kernel deadlock-free, and tests/test_dag_order_cpu.py checks it
+// exhaustively through fgp_test_dag_order.
+__host__ __device__ inline void dag_decode_task(int task, int T, int B, int G, int matrixMajor, int& i, int& j, int& b) {
+    int qg = 0;
+    long pre = 0;
+    for (;;) {
+        const long cnt = (long)B * (G * (G + 1) / 2 + (T - (qg + 1) * G) * G);
+        if ((long)task < pre + cnt) break;
+        pre += cnt; ++qg;
+    }
+    int local = (int)((long)task - pre);
+    const int j0 = qg * G;
+    int rr = 0;
+    while (rr < G && local >= B * (rr + 1)) { local -= B * (rr + 1); ++rr; }
+    if (rr < G) { i = j0 + rr; b = local / (rr + 1); j = j0 + local - b * (rr + 1); }
+    else if (matrixMajor) {
+        const int perB = (T - j0 - G) * G;
+        b = local / perB;
+        const int l2 = local - b * perB;
+        i = j0 + G + l2 / G; j = j0 + l2 - (l2 / G) * G;
+    } else {
+        const int per = B * G;
+        i = j0 + G + local / per;
+        const int l2 = local - (local / per) * per;
+        b = l2 / G; j = j0 + l2 - b * G;
+    }
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
@@ -206,37 +242,8 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 #ifdef FGP_DAG_PROF
         long long tPh = clock64();
 #endif
-        // Claim order: groups of G tile columns; inside a group row by row, inside a row matrix by matrix, and for each
-        // the (up to G) tiles of the row.  G = 1 is plain column order.  With G > 1 the tiles (i, j), (i, j+1), ... of one
-        // row run side by side on neighbouring CTAs and stream the same L(i, :) chunks at the same time (one HBM read,
-        // G - 1 L2 hits), at the price of a short wait at their ends (tile (i, j+1) needs L(i, j)).
-        const int G = g.G;
-        int qg = 0;
-        long pre = 0;
-        for (;;) {
-            const long cnt = (long)B * (G * (G + 1) / 2 + (T - (qg + 1) * G) * G);
-            if ((long)task < pre + cnt) break;
-            pre += cnt; ++qg;
-        }
-        int local = (int)((long)task - pre);
-        const int j0 = qg * G;
         int i, j, b;
-        int rr = 0;
-        while (rr < G && local >= B * (rr + 1)) { local -= B * (rr + 1); ++rr; }
-        if (rr < G) { i = j0 + rr; b = local / (rr + 1); j = j0 + local - b * (rr + 1); }
-        else if (g.matrixMajor) {
-            // below the group's triangle: matrix by matrix, inside a matrix row by row -- tiles that read the same L(j, :)
-            // are claimed back to back, start within microseconds of each other and share its chunks in L2
-            const int perB = (T - j0 - G) * G;
-            b = local / perB;
-            const int l2 = local - b * perB;
-            i = j0 + G + l2 / G; j = j0 + l2 - (l2 / G) * G;
-        } else {
-            const int per = B * G;
-            i = j0 + G + local / per;
-            const int l2 = local - (local / per) * per;
-            b = l2 / G; j = j0 + l2 - b * G;
-        }
+        dag_decode_task(task, T, B, g.G, g.matrixMajor, i, j, b);
         const bool diag = i == j;
         const int rowBase = i * FGP_TILE, colBase = j * FGP_TILE;
         double* C = g.M + (long)b * g.strideM;
@@ -520,6 +527,15 @@ extern "C" void fgp_dag_prof_read(unsigned long long* out8, int reset) {
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_dag_prof, z, sizeof(z)); }
 }
 #endif
+
+// test support (CPU gate): the claim order of the dataflow kernel, so that its topological property can be checked without a GPU
+extern "C" int fgp_test_dag_order(int T, int B, int G, int matrixMajor, int task, int* i, int* j, int* b) {
+    if (T <= 0 || B <= 0 || G <= 0 || T % G != 0 || !i || !j || !b) return -1;
+    const long ntasks = (long)B * T * (T + 1) / 2;
+    if (task < 0 || task >= ntasks) return -1;
+    dag_decode_task(task, T, B, G, matrixMajor, *i, *j, *b);
+    return 0;
+}
 
 bool chol_dag_supported(int n, int nrows) { return n > 0 && nrows == n + 1; }
 

@@ -61,6 +61,11 @@ int fgp_project(fgp_ctx* ctx, const double* f, int n, int k, int p, int basis_ty
  * them against the oracle on a machine without a GPU.  fgp_project itself fails without a context. */
 int fgp_test_project_host(const double* f, int n, int k, int p, int basis_type, const double* B_in, double* B_out,
                           double* J_out, double* coefs_out);
+/* Test support, called by nothing in the product: the claim order of the persistent factorisation kernel
+ * (csrc/chol_dag.cu) -- task number -> (tile row, tile column, matrix) for T tile columns, B matrices, claim groups of G
+ * columns (G divides T).  tests/test_dag_order_cpu.py checks that every task only depends on tasks with smaller numbers
+ * (the kernel's spin-waits are deadlock-free exactly then).  Returns 0, or -1 for arguments out of range. */
+int fgp_test_dag_order(int T, int B, int G, int matrixMajor, int task, int* i, int* j, int* b);
 
 /* ---- problem = what setDistMatrix_S / setDistMatrix_F are given (R/7_distanceFunctions.R:3-22) ---- */
 /* sIn n x ds (may be NULL when ds = 0); for each functional input i: coefs[i] n x p[i], J[i] p[i] x p[i],
