@@ -761,3 +761,29 @@ def test_dataflow_cholesky_is_bit_identical(ctx, n, B):
     r_nll, _ = ref.negLogLik(thB[:, 0], [], Ms, case["y"], "matern3_2", 1e-8)
     assert abs(out[1][0][0] - r_nll) <= _nll_tol(r_nll, n)
     P.close()
+
+
+def test_dataflow_cholesky_is_bit_identical_at_size(ctx):
+    """The same engine comparison at the bench size (n = 8192: 64 tile columns, 2080 tile tasks per matrix, every CTA runs
+    many tasks and most waits are on the chain) -- single evaluation (claim on demand) and a batch of 5 (claim ahead),
+    and a ragged neighbour (n = 8000)."""
+    import fungp_b200
+    from fungp_b200 import synth
+    for n in (8192, 8000):
+        sIn, fIn, y = synth.make_data(n, n, 4, [100, 100])
+        proj = [ctx.project(f, 5, "B-splines") for f in fIn]
+        P = fungp_b200.Problem(ctx, sIn, [c for (_, _, c) in proj], [j for (_, j, _) in proj], ["L2_bygroup"] * 2, y)
+        ub = 2.0 * P.dist_max()
+        out = {}
+        try:
+            for dag in (0, 1):
+                ctx.set_option("dag", dag)
+                one = P.nll_batch("gauss", 1e-8, 0.25 * ub)
+                five = P.nll_batch("matern5_2", 1e-8, np.stack([0.25 * ub * (1 + 0.01 * i) for i in range(5)], axis=1))
+                out[dag] = (one[0], one[1], one[2], five[0], five[1], five[2])
+        finally:
+            ctx.set_option("dag", 1)
+        for a, b in zip(out[0], out[1]):
+            assert np.array_equal(a, b)
+        assert not out[1][2].any() and not out[1][5].any() and np.all(np.isfinite(out[1][3]))
+        P.close()
