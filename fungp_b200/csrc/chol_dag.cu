@@ -67,6 +67,9 @@ struct DagArgs {
     int batch, T, n;               // T = n / 128 tile rows and columns; the y row (row n) rides along in the diagonal tasks
     int G;                         // tile columns per claim group (divides T)
     int matrixMajor;               // claim order below the diagonal tiles of a group: 1 = matrix, row; 0 = row, matrix
+    int hasY;                      // 1: row n holds y' and is solved along (likelihood, preMats); 0: a plain n x n matrix
+    // solve mode (predict / simulate: E tiles of extra rows from row rowOff on against the T prefactored column tiles)
+    int rowOff, mExtra, E;
     double* W; long strideW;
     int* info;
     int* flagL;                    // [batch][T][T]  L(i,j) stored
@@ -180,7 +183,7 @@ __device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* inf
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release(flagW, 1);
-    if (threadIdx.x < nb) {
+    if (yOut && threadIdx.x < nb) {
         const int c = threadIdx.x;
         const double* Tc = smem + c * potf2::LDT;                 // strict upper part of column c: E(k, c) = W(c, k), k < c
         const double* dinvE = smem + potf2::NB * potf2::LDT + potf2::SB * potf2::XLD + potf2::SB * potf2::ELD;
@@ -195,6 +198,9 @@ __device__ __noinline__ void diag_epilogue(double* smem, uint32_t pbar, int* inf
     potf2::store_L(smem, Mdiag, ld, nb);
 }
 
+// MODE 0: factorisation; MODE 1: solve mode (extra rows against the prefactored columns).  A template parameter, not a field:
+// the extra branches cost the tile loop of the factorisation registers it does not have (255, spills in the DMMA loop).
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __grid_constant__ CUtensorMap mapW) {
     extern __shared__ __align__(128) double smem[];
@@ -243,11 +249,15 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         long long tPh = clock64();
 #endif
         int i, j, b;
-        dag_decode_task(task, T, B, g.G, g.matrixMajor, i, j, b);
-        const bool diag = i == j;
-        const int rowBase = i * FGP_TILE, colBase = j * FGP_TILE;
+        constexpr bool extra = MODE != 0;
+        if (!extra) dag_decode_task(task, T, B, g.G, g.matrixMajor, i, j, b);
+        else { j = task / g.E; i = T + (task - j * g.E); b = 0; }     // solve mode: column by column, the E row tiles of each
+        const bool diag = !extra && i == j;
+        const int rowBase = extra ? g.rowOff + (i - T) * FGP_TILE : i * FGP_TILE, colBase = j * FGP_TILE;
         double* C = g.M + (long)b * g.strideM;
-        const int* fLi = g.flagL + ((long)b * T + i) * T;
+        // ready flags of this tile's own row; in solve mode the factor's tiles (and every W_j) are there from the start
+        int* fLrow = extra ? g.flagL + (long)(i - T) * T : g.flagL + ((long)b * T + i) * T;
+        const int* fLi = fLrow;
         const int* fLj = g.flagL + ((long)b * T + j) * T;
         const int* fY = g.flagY + (long)b * T;
         const int nchunks = j * (FGP_TILE / KC);
@@ -256,8 +266,10 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         bool ready = true;
         for (int kt = tid; kt < j; kt += THREADS) {
             ready = ready && ld_acquire(fLi + kt) != 0;
-            if (!diag) ready = ready && ld_acquire(fLj + kt) != 0;
-            else ready = ready && ld_acquire(fY + kt) != 0;
+            if (!extra) {
+                if (!diag) ready = ready && ld_acquire(fLj + kt) != 0;
+                else if (g.hasY) ready = ready && ld_acquire(fY + kt) != 0;
+            }
         }
         const bool allReady = __syncthreads_and(ready) != 0;
 #ifdef FGP_DAG_PROF
@@ -268,12 +280,13 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         // diagonal tiles: the two warps that lie entirely above the diagonal carry the y row instead -- 64 columns each,
         // two per lane: ay(c) -= sum_k y(k) L(j-tile row c, k), FMAs in k order on the B slabs that pass through the ring
         const bool active = !(diag && (wm * 32 + 31 < wn * 64));
-        const bool ywarp = diag && !active;
+        const bool ywarp = diag && !active && g.hasY;
         const int ycol = (wm == 0 ? 0 : 64) + lane;
         const double* yrow = C + g.n;                                    // element k of the y row: yrow[k * ld]
         double ay0 = 0.0, ay1 = 0.0;
         // ragged last tile row / column (n not a multiple of 128): rows and columns from n on do not exist
-        const int nbRows = min(FGP_TILE, g.n - rowBase), nbCols = min(FGP_TILE, g.n - colBase);
+        const int nbRows = extra ? min(FGP_TILE, g.mExtra - (i - T) * FGP_TILE) : min(FGP_TILE, g.n - rowBase);
+        const int nbCols = min(FGP_TILE, g.n - colBase);
         const bool fullTile = nbRows == FGP_TILE && nbCols == FGP_TILE;
         if (ywarp) {
             if (ycol < nbCols) ay0 = __ldcg(yrow + (long)(colBase + ycol) * g.ld);
@@ -285,7 +298,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         auto issue = [&](int cl, int G) {
             if (!allReady && (cl & 3) == 0) {
                 wait_flag(fLi + (cl >> 2));
-                if (!diag) wait_flag(fLj + (cl >> 2));
+                if (!diag && !extra) wait_flag(fLj + (cl >> 2));
             }
             const int sn = G % STAGES;
             if (G >= STAGES) mbar_wait(emptyB + 8 * sn, ((G / STAGES) - 1) & 1);
@@ -396,7 +409,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                         // potf2's input: the lower triangle of the nb x nb block, identity padding, zeros above the diagonal
                         if (r < c) v = 0.0;
                         else if (r >= nbRows || c >= nbCols) v = (r == c) ? 1.0 : 0.0;
-                    }
+                    } else if (extra && c >= nbCols) v = 0.0;      // solve mode, ragged last column tile: k beyond n does not exist
                     smem[c * PITCH + r] = v;
                 }
 
@@ -405,14 +418,14 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             __syncthreads();
             diag_epilogue(smem, pbar, g.info ? g.info + b : nullptr, colBase, C + (long)colBase + (long)colBase * g.ld, g.ld, nbCols,
                           g.W + (long)b * g.strideW + (long)j * FGP_TILE * FGP_TILE, g.flagW + (long)b * T + j, ay,
-                          C + g.n + (long)colBase * g.ld, g.flagY + (long)b * T + j);
+                          g.hasY ? C + g.n + (long)colBase * g.ld : nullptr, g.flagY + (long)b * T + j);
             __syncthreads();     // the hand-over area is free again
         } else {
             // ---- L(i,j) = acc W_j'   (W_j lower triangular: W(c, k) = 0 for k > c, so an 8-column block of the result
             //      needs k up to its last column only -- the zero products are skipped, block by block)
             const uint32_t wslab = sbase + (uint32_t)(2 * STAGE * 8);
             if (producer) {
-                wait_flag(g.flagW + (long)b * T + j);
+                if (!extra) wait_flag(g.flagW + (long)b * T + j);
 #pragma unroll
                 for (int cw = 0; cw < 2; ++cw) {
                     mbar_expect_tx(wfullB + 8 * cw, SLAB_TX);
@@ -474,14 +487,15 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
                         Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
                         Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
                     }
-            } else {         // last tile row: rows from n on do not exist (off-diagonal tiles always have all 128 columns)
+            } else {         // ragged tile: rows / columns beyond the matrix do not exist
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
                     for (int mi = 0; mi < 4; ++mi)
                         if (wm * 32 + mi * 8 + r_lane < nbRows) {
-                            Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];
-                            Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];
+                            const int cl = wn * 64 + ni * 8 + c_lane;
+                            if (!extra || cl < nbCols) Cw[mi * 8 + (long)(ni * 8) * g.ld] = acc[mi][ni][0];        // (factorisation:
+                            if (!extra || cl + 1 < nbCols) Cw[mi * 8 + (long)(ni * 8 + 1) * g.ld] = acc[mi][ni][1];   //  all 128 columns exist)
                         }
             }
             __threadfence();
@@ -489,7 +503,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 #ifdef FGP_DAG_PROF
             DPROF(10, tS);
 #endif
-            if (producer) st_release(g.flagL + ((long)b * T + i) * T + j, 1);
+            if (producer) st_release(fLrow + j, 1);
         }
         if (producer && !claimAhead) sTask[(it + 1) & 1] = atomicAdd(g.counter, 1);
         __syncthreads();
@@ -537,21 +551,21 @@ extern "C" int fgp_test_dag_order(int T, int B, int G, int matrixMajor, int task
     return 0;
 }
 
-bool chol_dag_supported(int n, int nrows) { return n > 0 && nrows == n + 1; }
+bool chol_dag_supported(int n, int nrows) { return n > 0 && (nrows == n + 1 || nrows == n); }
 
 size_t chol_dag_flag_bytes(int n, int batch) {
     const size_t T = ((size_t)n + FGP_TILE - 1) / FGP_TILE;
     return sizeof(int) * ((size_t)batch * T * T + 2 * (size_t)batch * T + 4);
 }
+size_t chol_dag_solve_flag_bytes(int n, int mExtra) {
+    const size_t T = ((size_t)n + FGP_TILE - 1) / FGP_TILE, E = ((size_t)mExtra + FGP_TILE - 1) / FGP_TILE;
+    return sizeof(int) * (E * T + 4);
+}
 
-// Factors the `batch` trapezoids at M (n columns, n + 1 rows: the y row rides along, leading dimension ld) in place, W
-// receives the inverse diagonal blocks, info the failing minor orders.  flags: chol_dag_flag_bytes() of device memory.
-// Returns false when the launch cannot be taken (driver entry point missing, alignment) -- the caller then runs chol.cu.
-bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
-                     cudaStream_t st, int group, int matrixMajor) {
+namespace {
+bool dag_prepare(int* dev_out, int* sms_out) {
     static bool attr_set[FGP_MAXDEV] = {false};
     static int nsm[FGP_MAXDEV] = {0};
-    if (!chol_dag_supported(n, n + 1) || batch <= 0) return false;
     if (!g_encode_tried) {
         g_encode_tried = true;
         void* fn = nullptr;
@@ -561,23 +575,39 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
         else cudaGetLastError();
     }
     if (!g_encode) return false;
-    if (((uintptr_t)M & 15) || ((uintptr_t)W & 15) || (ld & 1) || (strideM & 1) || (strideW & 1)) return false;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= FGP_MAXDEV) dev = 0;
     if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(chol_dag_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(chol_dag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
         attr_set[dev] = true;
     }
+    *dev_out = dev;
+    *sms_out = nsm[dev] > 0 ? nsm[dev] : 148;
+    return true;
+}
+}  // namespace
+
+// Factors the `batch` matrices at M (n columns, leading dimension ld; hasY: n + 1 rows, the y row rides along) in place, W
+// receives the inverse diagonal blocks, info the failing minor orders.  flags: chol_dag_flag_bytes() of device memory.
+// Returns false when the launch cannot be taken (driver entry point missing, alignment) -- the caller then runs chol.cu.
+bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
+                     cudaStream_t st, int group, int matrixMajor, int hasY) {
+    if (n <= 0 || batch <= 0) return false;
+    int dev, sms;
+    if (!dag_prepare(&dev, &sms)) return false;
+    if (((uintptr_t)M & 15) || ((uintptr_t)W & 15) || (ld & 1) || (strideM & 1) || (strideW & 1)) return false;
     DagArgs g{};
     g.M = M; g.ld = ld; g.strideM = strideM; g.batch = batch;
     g.T = (n + FGP_TILE - 1) / FGP_TILE; g.n = n;
     g.G = (group > 1 && g.T % group == 0) ? group : 1;
     g.matrixMajor = matrixMajor;
+    g.hasY = hasY ? 1 : 0;
     g.W = W; g.strideW = strideW; g.info = info;
     const size_t nL = (size_t)batch * g.T * g.T, nW = (size_t)batch * g.T;
     g.flagL = (int*)flags; g.flagW = g.flagL + nL; g.flagY = g.flagW + nW; g.counter = g.flagY + nW;
@@ -585,11 +615,39 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
     if (perMatrix * batch > 0x7fffffffL / 2) return false;
     g.ntasks = (int)(perMatrix * batch);
     CUtensorMap mapM, mapW;
-    if (!make_map(&mapM, M, n + 1, n, ld, batch, strideM)) return false;
+    if (!make_map(&mapM, M, n + (hasY ? 1 : 0), n, ld, batch, strideM)) return false;
     if (!make_map(&mapW, W, FGP_TILE, (long)g.T * FGP_TILE, FGP_TILE, batch, strideW)) return false;      // W_j unit-padded: always 128 x 128
     if (cudaMemsetAsync(flags, 0, chol_dag_flag_bytes(n, batch), st) != cudaSuccess) { cudaGetLastError(); return false; }
-    const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
     FGP_COUNT_LAUNCH();
-    chol_dag_kernel<<<std::min(sms, g.ntasks), THREADS, DAG_SMEM, st>>>(g, mapM, mapW);
+    chol_dag_kernel<0><<<std::min(sms, g.ntasks), THREADS, DAG_SMEM, st>>>(g, mapM, mapW);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+// Solve mode (predict / simulate, R/4_prediction_SF.R:9, R/5_simulation_SF.R:10): the mExtra rows from row rowOff on of M
+// (n columns: K(new, train)) against the factor stored in rows 0..n-1 of the same matrix and its inverse diagonal blocks
+// W -> L^-1 K(train, new) transposed, in place.  One tile task per (row tile of the block, column tile): it accumulates
+// -= X(r, 0:j) L(j, 0:j)' as the tiles of its own row are flagged and multiplies by W_j'.  flags:
+// chol_dag_solve_flag_bytes().  Returns false when the launch cannot be taken.
+bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, double* W, void* flags, cudaStream_t st) {
+    if (n <= 0 || mExtra <= 0 || rowOff < n) return false;
+    int dev, sms;
+    if (!dag_prepare(&dev, &sms)) return false;
+    if (((uintptr_t)M & 15) || ((uintptr_t)W & 15) || (ld & 1)) return false;
+    DagArgs g{};
+    g.M = M; g.ld = ld; g.strideM = 0; g.batch = 1;
+    g.T = (n + FGP_TILE - 1) / FGP_TILE; g.n = n;
+    g.G = 1; g.matrixMajor = 1; g.hasY = 0;
+    g.rowOff = rowOff; g.mExtra = mExtra; g.E = (mExtra + FGP_TILE - 1) / FGP_TILE;
+    g.W = W; g.strideW = 0; g.info = nullptr;
+    g.flagL = (int*)flags; g.flagW = g.flagL; g.flagY = g.flagL; g.counter = g.flagL + (size_t)g.E * g.T;
+    if ((long)g.T * g.E > 0x7fffffffL / 2) return false;
+    g.ntasks = g.T * g.E;
+    if (g.ntasks < 16) return false;      // a handful of tiles: the fixed costs of the persistent launch do not pay (measured: n = 1000, m = 10)
+    CUtensorMap mapM, mapW;
+    if (!make_map(&mapM, M, (long)rowOff + mExtra, n, ld, 1, 0)) return false;
+    if (!make_map(&mapW, W, FGP_TILE, (long)g.T * FGP_TILE, FGP_TILE, 1, 0)) return false;
+    if (cudaMemsetAsync(flags, 0, chol_dag_solve_flag_bytes(n, mExtra), st) != cudaSuccess) { cudaGetLastError(); return false; }
+    FGP_COUNT_LAUNCH();
+    chol_dag_kernel<1><<<std::min(sms, g.ntasks), THREADS, DAG_SMEM, st>>>(g, mapM, mapW);
     return cudaGetLastError() == cudaSuccess;
 }

@@ -111,11 +111,14 @@ int trap_factor(fgp_ctx* ctx, int devslot, const TrapDesc& t, cudaStream_t sPane
 void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, double* W, long strideW, int* info,
                   int infoBase, cudaStream_t st, int pdl = 0);
 
-// the whole factorisation of a batch as one persistent dataflow kernel (chol_dag.cu); n a multiple of 128
+// the whole factorisation of a batch as one persistent dataflow kernel (chol_dag.cu): any n; nrows == n + 1 (the y row
+// rides along) or nrows == n (hasY = 0); and its solve mode for the extra rows of predict / simulate
 bool chol_dag_supported(int n, int nrows);
 size_t chol_dag_flag_bytes(int n, int batch);
+size_t chol_dag_solve_flag_bytes(int n, int mExtra);
 bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
-                     cudaStream_t st, int group = 1, int matrixMajor = 1);
+                     cudaStream_t st, int group = 1, int matrixMajor = 1, int hasY = 1);
+bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, double* W, void* flags, cudaStream_t st);
 
 struct GemmArgs {
     const double* A; long lda; long strideA;   // row operand: element (r, kk) = A[r + kk*lda], r = global row

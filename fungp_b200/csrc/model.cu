@@ -318,8 +318,12 @@ extern "C" int fgp_predict(fgp_problem* P, int m, const double* sNew, const doub
         t.M = pd.Lfac; t.ld = ld; t.strideM = 0; t.batch = 1;
         t.ncols = n; t.nrows = holeHi + mc; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
         t.cpre = cdiv(n, FGP_TILE); t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
-        rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
-        if (rc) return rc;
+        // solve mode of the dataflow kernel (one launch), else the launch-per-step schedule with every tile prefactored
+        if (!(ctx->dag && !ctx->profile && !d.dagFlags.ensure(chol_dag_solve_flag_bytes(n, mc)) &&
+              launch_chol_dag_solve(pd.Lfac, ld, n, holeHi, mc, pd.Wall, d.dagFlags.p, st))) {
+            rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);
+            if (rc) return rc;
+        }
         // mean = LInvK' LInvY ; |LInvK_i|^2 for sd     (R/4_prediction_SF.R:10-11)
         launch_rowstats(pd.Lfac, ld, 0, 1, holeHi, mc, n, 0, pd.Lfac + n, ld, 0, dNorm + c0, dMean + c0, st);
     }
@@ -466,8 +470,11 @@ extern "C" int fgp_simulate(fgp_problem* P, int m, const double* sNew, const dou
     t.M = pd.Lfac; t.ld = ld; t.strideM = 0; t.batch = 1;
     t.ncols = n; t.nrows = holeHi + m; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
     t.cpre = cdiv(n, FGP_TILE); t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
-    rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);      // LInvK' in the rows under the factor (:10)
-    if (rc) return rc;
+    if (!(ctx->dag && !ctx->profile && !d.dagFlags.ensure(chol_dag_solve_flag_bytes(n, m)) &&
+          launch_chol_dag_solve(pd.Lfac, ld, n, holeHi, m, pd.Wall, d.dagFlags.p, st))) {
+        rc = trap_factor(ctx, 0, t, st, d.sBulk, ctx->lookahead != 0);  // LInvK' in the rows under the factor (:10)
+        if (rc) return rc;
+    }
     launch_rowstats(pd.Lfac, ld, 0, 1, holeHi, m, n, 0, pd.Lfac + n, ld, 0, dNorm, dMean, st);
     // K.ss - t(LInvK) LInvK: one symmetric update with K = n                                     (:14)
     launch_gemm_plain(pd.Lfac + holeHi, ld, pd.Lfac + holeHi, ld, Css, ldc, m, m, n, true, st);
@@ -475,8 +482,12 @@ extern "C" int fgp_simulate(fgp_problem* P, int m, const double* sNew, const dou
     c.M = Css; c.ld = ldc; c.strideM = 0; c.batch = 1;
     c.ncols = m; c.nrows = m; c.holeLo = m; c.holeHi = m; c.colHoleLo = m; c.colHoleHi = m;
     c.cpre = 0; c.upperRows = 0; c.W = (double*)d.wbuf.p; c.strideW = 0; c.info = dInfo;
-    rc = trap_factor(ctx, 0, c, st, d.sBulk, ctx->lookahead != 0);      // chol of the conditional covariance
-    if (rc) return rc;
+    // chol of the conditional covariance: a plain m x m matrix (no y row)
+    if (!(ctx->dag && !ctx->profile && !d.dagFlags.ensure(chol_dag_flag_bytes(m, 1)) &&
+          launch_chol_dag(c.M, c.ld, 0, 1, m, c.W, 0, c.info, d.dagFlags.p, st, 1, ctx->dag_order, 0))) {
+        rc = trap_factor(ctx, 0, c, st, d.sBulk, ctx->lookahead != 0);
+        if (rc) return rc;
+    }
     // sims = mean + (Lc Z)'  as  sims(s, i) = mean_i - sum_j (-Z')(s, j) Lc(i, j)
     launch_zero_strict_upper(Css, ldc, m, st);
     launch_bcast_rows(dSims, nsim, nsim, m, dMean, st);

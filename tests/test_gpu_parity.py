@@ -787,3 +787,36 @@ def test_dataflow_cholesky_is_bit_identical_at_size(ctx):
             assert np.array_equal(a, b)
         assert not out[1][2].any() and not out[1][5].any() and np.all(np.isfinite(out[1][3]))
         P.close()
+
+
+@pytest.mark.parametrize("n,m", [(1407, 300), (2048, 130), (640, 1000)])
+def test_dataflow_solve_mode_is_bit_identical(ctx, n, m):
+    """predict / simulate: the rows of K(new, train) under the stored factor are eliminated by the solve mode of the
+    dataflow kernel (one tile task per (row tile, column tile), flags between the tiles of a row) or, with the option
+    dag 0, launch by launch with every column tile prefactored.  Same fused multiply-adds in the same order: mean, sd and
+    simulations agree to the last bit -- ragged n (masked last column tile), ragged m, more new points than training
+    points; and mean / sd against the oracle."""
+    seed = 500 + n
+    case = make_case(seed, n, 2, [25, 18], [3, 2], ["B-splines", "PCA"], ["L2_bygroup", "L2_byindex"], extra=m)
+    P = _problem(ctx, case)
+    theta = 0.3 * 2.0 * P.dist_max()
+    _, s2, info = P.nll_batch("matern5_2", 1e-8, theta)
+    assert info[0] == 0
+    Z = np.random.default_rng(seed).standard_normal((m, 3))
+    out = {}
+    try:
+        for dag in (0, 1):
+            ctx.set_option("dag", dag)
+            L, z = P.premats("matern5_2", 1e-8, s2[0], theta)
+            pr = P.predict(m, case["sNew"], case["coefsNew"])
+            sm = P.simulate(m, Z, case["sNew"], case["coefsNew"], nugget_sm=1e-8)
+            out[dag] = (L, z, pr["mean"], pr["sd"], sm["sims"], sm["mean"], sm["sd"])
+    finally:
+        ctx.set_option("dag", 1)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    Mtp, _ = oracle_dists(case, new=True)
+    po = ref.makePreds(Mtp, None, s2[0], theta, "matern5_2", out[1][0], out[1][1], "light", 1e-8)
+    assert np.max(np.abs(out[1][2] - po["mean"])) <= 1e-8 * max(1.0, np.max(np.abs(po["mean"])))
+    assert np.max(np.abs(out[1][3] - po["sd"])) <= 1e-8 * np.sqrt(s2[0]) + 1e-8 * np.max(po["sd"])
+    P.close()
