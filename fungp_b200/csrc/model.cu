@@ -618,8 +618,12 @@ extern "C" int fgp_update_y(fgp_problem* P, const double* y_new, double* LInvY_o
     t.M = pd.Lfac; t.ld = pd.ldL; t.strideM = 0; t.batch = 1;
     t.ncols = n; t.nrows = holeHi + 1; t.holeLo = n; t.holeHi = holeHi; t.colHoleLo = n; t.colHoleHi = n;
     t.cpre = cdiv(n, FGP_TILE); t.upperRows = 0; t.W = pd.Wall; t.strideW = 0; t.info = dInfo;
-    rc = trap_factor(ctx, 0, t, st, d.sBulk, false);
-    if (rc) return rc;
+    // the one row through the solve mode of the dataflow kernel (from 16 column tiles on), else launch by launch
+    if (!(ctx->dag && !ctx->profile && !d.dagFlags.ensure(chol_dag_solve_flag_bytes(n, 1)) &&
+          launch_chol_dag_solve(pd.Lfac, pd.ldL, n, holeHi, 1, pd.Wall, d.dagFlags.p, st))) {
+        rc = trap_factor(ctx, 0, t, st, d.sBulk, false);
+        if (rc) return rc;
+    }
     launch_copy_row(pd.Lfac, pd.ldL, n, holeHi, n, st);
     CK(wait_stream(ctx, d, st));
     CK(cudaGetLastError());
