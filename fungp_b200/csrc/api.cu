@@ -516,7 +516,8 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
         // the workspaces must grow: size the chunk against what the device has left (not on the steady-state path)
         size_t freeB = 0, totB = 0;
         cudaMemGetInfo(&freeB, &totB);
-        const size_t budget = std::min<size_t>((size_t)((freeB + d.work.cap + d.wbuf.cap) * 0.6), (size_t)32 << 30);
+        // at most 60 % of what the device has left, and 64 GB (of 180): 7 full-storage matrices of n = 32768 per chunk
+        const size_t budget = std::min<size_t>((size_t)((freeB + d.work.cap + d.wbuf.cap) * 0.6), (size_t)64 << 30);
         chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)chunk, budget / (matBytes + wBytes)));
     }
     if (d.work.ensure(matBytes * chunk) || d.wbuf.ensure(wBytes * chunk)) {
