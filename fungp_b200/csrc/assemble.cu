@@ -20,6 +20,7 @@
 // coordinate and entry plus an 18-instruction exp against 8 bytes written, on a machine whose DFMA and DMMA share
 // one FP64 datapath (profiles/r01_peaks.md) -- see DESIGN.md 2.3 for the count.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -330,10 +331,16 @@ struct FusedK {
     int count;
 };
 
+// Persistent: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of ONE group.  The unit table and -- for
+// groups of at most FBCH elements -- the multipliers are staged once per CTA, and the coordinates of the next tile are
+// fetched with cp.async into the second half of a double buffer while the B passes over the current tile run: the
+// per-tile set-up (three dependent global round trips, measured at ~3.7 passes' worth) is off the critical path.
 template <int KER>
-__global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
-    __shared__ __align__(16) double sP[FCC][FR];
-    __shared__ __align__(16) double sQ[FCC][FC];
+__global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k, int ntiles) {
+    // double-buffered coordinates in dynamic shared memory (60 KB: above the static limit): sP[2][FCC][FR] | sQ[2][FCC][FC]
+    extern __shared__ __align__(16) double fusedDyn[];
+    double (*sP)[FCC][FR] = reinterpret_cast<double (*)[FCC][FR]>(fusedDyn);
+    double (*sQ)[FCC][FC] = reinterpret_cast<double (*)[FCC][FC]>(fusedDyn + 2 * FCC * FR);
     __shared__ __align__(16) double sSc[FBCH][FNT];   // gauss: -scale^2 / 2 (multiplies squared differences); Matern: scale
     __shared__ __align__(16) double sSc2[KER == 2 ? FBCH : 1][FNT];   // matern5_2: scale^2 / 3
     __shared__ int sCol[FCC], sFlag[FCC], sTermFirst[FNT + 1], sNterms;
@@ -343,13 +350,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
     const AsmArgs& a = k.a;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;             // rows 4tx..4tx+3, column ty
-    // tile (I over 64-row blocks, J over 16-column blocks) with J < R (I + 1), R = FR / FC:  t = R I (I + 1) / 2 + J
     constexpr int R = FR / FC;
-    int I = (int)((sqrtf(8.0f * (float)blockIdx.x / (float)R + 1.0f) - 1.0f) * 0.5f);
-    while (R * (I + 1) * (I + 2) / 2 <= (int)blockIdx.x) ++I;
-    while (R * I * (I + 1) / 2 > (int)blockIdx.x) --I;
-    const int J = blockIdx.x - R * I * (I + 1) / 2;
-    const int i0 = I * FR, j0 = J * FC;
     AsmGroup g;
     if (k.groups) g = k.groups[blockIdx.y];
     else { g.first = 0; g.count = k.count; }
@@ -372,60 +373,35 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
         if (l1) sTermFirst[__popc(m0) + __popc(m1 & below) + 1] = tid + 33;
         if (tid == 0) { sTermFirst[0] = 0; sNterms = __popc(m0) + __popc(m1); }
     }
-    for (int idx = tid; idx < nunits * FR; idx += FTHREADS) {
-        const int c = idx / FR, pnt = idx % FR;
-        sP[c][pnt] = (i0 + pnt < a.nP) ? X[(long)sCol[c] * a.ldP + i0 + pnt] : 0.0;
-    }
-    for (int idx = tid; idx < nunits * FC; idx += FTHREADS) {
-        const int c = idx / FC, pnt = idx % FC;
-        sQ[c][pnt] = (j0 + pnt < a.nQ) ? X[(long)sCol[c] * a.ldQ + j0 + pnt] : 0.0;
-    }
-    __syncthreads();
-    const int nterms = sNterms;
-
-    // ---- base quantity of every term: |x_i - x_j|, or the summed squares (gauss) / their root (Matern) of a group
-    double q[4][FNT];
-#pragma unroll
-    for (int t = 0; t < FNT; ++t) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) q[i][t] = 0.0;
-        if (t < nterms) {
-            const int u0 = sTermFirst[t], u1 = sTermFirst[t + 1];
-            if (!(sFlag[u0] & 1)) {
-                const double2 p01 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx]);
-                const double2 p23 = *reinterpret_cast<const double2*>(&sP[u0][4 * tx + 2]);
-                const double xq = sQ[u0][ty];
-                q[0][t] = fabs(p01.x - xq); q[1][t] = fabs(p01.y - xq); q[2][t] = fabs(p23.x - xq); q[3][t] = fabs(p23.y - xq);
-                if (KER == 1) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) q[i][t] = __dmul_rn(q[i][t], q[i][t]);
-                }
-            } else {
-                double D2[4] = {0.0, 0.0, 0.0, 0.0};
-                for (int u = u0; u < u1; ++u) {
-                    const double2 p01 = *reinterpret_cast<const double2*>(&sP[u][4 * tx]);
-                    const double2 p23 = *reinterpret_cast<const double2*>(&sP[u][4 * tx + 2]);
-                    const double xq = sQ[u][ty];
-                    const double d0 = p01.x - xq, d1 = p01.y - xq, d2 = p23.x - xq, d3 = p23.y - xq;
-                    D2[0] = fma(d0, d0, D2[0]); D2[1] = fma(d1, d1, D2[1]); D2[2] = fma(d2, d2, D2[2]); D2[3] = fma(d3, d3, D2[3]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) q[i][t] = (KER == 1) ? D2[i] : sqrt(D2[i]);
-            }
+    // tile t -> (I over 64-row blocks, J over 16-column blocks) with J < R (I + 1):  t = R I (I + 1) / 2 + J
+    auto tile_origin = [&](int t, int& i0, int& j0) {
+        int I = (int)((sqrtf(8.0f * (float)t / (float)R + 1.0f) - 1.0f) * 0.5f);
+        while (R * (I + 1) * (I + 2) / 2 <= t) ++I;
+        while (R * I * (I + 1) / 2 > t) --I;
+        i0 = I * FR; j0 = (t - R * I * (I + 1) / 2) * FC;
+    };
+    // coordinates of a tile's 64 + 16 points, every unit: asynchronous 8-byte copies (zeros beyond the last point)
+    auto fetch = [&](int t, int buf) {
+        int i0, j0;
+        tile_origin(t, i0, j0);
+        for (int idx = tid; idx < nunits * FR; idx += FTHREADS) {
+            const int c = idx / FR, pnt = idx % FR;
+            if (i0 + pnt < a.nP) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sP[buf][c][pnt]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(X + (long)sCol[c] * a.ldP + i0 + pnt));
+            } else sP[buf][c][pnt] = 0.0;
         }
-    }
-
-    const bool scaled = a.mult != 1.0;
-    const int gi0 = i0 + 4 * tx, gj = j0 + ty;
-    // which of this thread's four entries lies on the diagonal of the matrix (0..3; anything else: none)
-    const unsigned dgi = (unsigned)((a.colOff + gj) - (a.rowOff + gi0));
-    const long colOffset = (long)(a.colOff + gj) * a.ld + a.rowOff + gi0;
-    // 16-byte stores need an aligned address in every matrix of the group: an even stride keeps the alignment of the first
-    const bool full4 = gi0 + 3 < a.nP && !(a.strideM & 1) &&
-                       ((reinterpret_cast<uintptr_t>(a.M + (long)g.first * a.strideM + colOffset) & 15) == 0);
-    for (int b0 = 0; b0 < g.count; b0 += FBCH) {
-        const int nb = min(FBCH, g.count - b0);
-        __syncthreads();
+        for (int idx = tid; idx < nunits * FC; idx += FTHREADS) {
+            const int c = idx / FC, pnt = idx % FC;
+            if (j0 + pnt < a.nQ) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sQ[buf][c][pnt]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(X + (long)sCol[c] * a.ldQ + j0 + pnt));
+            } else sQ[buf][c][pnt] = 0.0;
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    // multipliers of the batch elements [b0, b0 + nb)
+    auto stage_scales = [&](int b0, int nb, int nterms) {
         for (int idx = tid; idx < nb * FNT; idx += FTHREADS) {
             const int b = idx / FNT, t = idx % FNT;
             double sc = 0.0;
@@ -436,52 +412,118 @@ __global__ void __launch_bounds__(FTHREADS, 2) assemble_fused_kernel(FusedK k) {
             sSc[b][t] = (KER == 1) ? __dmul_rn(-0.5, __dmul_rn(sc, sc)) : sc;
             if (KER == 2) sSc2[b][t] = matern52_c2(sc);
         }
-        __syncthreads();
-        if (gj >= a.nQ) continue;
-        double* colp = a.M + (long)(g.first + b0) * a.strideM + colOffset;
-        for (int b = 0; b < nb; ++b, colp += a.strideM) {
-            double S[4] = {0.0, 0.0, 0.0, 0.0}, Pr[4] = {1.0, 1.0, 1.0, 1.0};
-            double scv[FNT];
+    };
+    __syncthreads();                                     // sCol, sNterms
+    const int nterms = sNterms;
+    const bool scalesOnce = g.count <= FBCH;
+    if (scalesOnce) stage_scales(0, g.count, nterms);
+    int tile = blockIdx.x;
+    if (tile < ntiles) fetch(tile, 0);
+    const bool scaled = a.mult != 1.0;
+
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                                 // this tile's coordinates (and, first time, the multipliers) are in; the
+                                                         // other buffer is no longer read
+        if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x, buf ^ 1);
+        int i0, j0;
+        tile_origin(tile, i0, j0);
+
+        // ---- base quantity of every term: |x_i - x_j| (squared for gauss), or the summed squares (gauss) / their root
+        //      (Matern) of a group
+        double q[4][FNT];
 #pragma unroll
-            for (int t = 0; t < FNT; t += 2) {
-                const double2 s2 = *reinterpret_cast<const double2*>(&sSc[b][t]);
-                scv[t] = s2.x; scv[t + 1] = s2.y;
-            }
+        for (int t = 0; t < FNT; ++t) {
 #pragma unroll
-            for (int t = 0; t < FNT; ++t) {
-                if (t < nterms) {
-                    const double sc = scv[t];
+            for (int i = 0; i < 4; ++i) q[i][t] = 0.0;
+            if (t < nterms) {
+                const int u0 = sTermFirst[t], u1 = sTermFirst[t + 1];
+                if (!(sFlag[u0] & 1)) {
+                    const double2 p01 = *reinterpret_cast<const double2*>(&sP[buf][u0][4 * tx]);
+                    const double2 p23 = *reinterpret_cast<const double2*>(&sP[buf][u0][4 * tx + 2]);
+                    const double xq = sQ[buf][u0][ty];
+                    q[0][t] = fabs(p01.x - xq); q[1][t] = fabs(p01.y - xq); q[2][t] = fabs(p23.x - xq); q[3][t] = fabs(p23.y - xq);
                     if (KER == 1) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) S[i] = fma(q[i][t], sc, S[i]);
-                    } else {
-                        const double c2 = (KER == 2) ? sSc2[KER == 2 ? b : 0][t] : 0.0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) matern_term<KER>(q[i][t], sc, c2, S[i], Pr[i]);
+                        for (int i = 0; i < 4; ++i) q[i][t] = __dmul_rn(q[i][t], q[i][t]);
                     }
+                } else {
+                    double D2[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int u = u0; u < u1; ++u) {
+                        const double2 p01 = *reinterpret_cast<const double2*>(&sP[buf][u][4 * tx]);
+                        const double2 p23 = *reinterpret_cast<const double2*>(&sP[buf][u][4 * tx + 2]);
+                        const double xq = sQ[buf][u][ty];
+                        const double d0 = p01.x - xq, d1 = p01.y - xq, d2 = p23.x - xq, d3 = p23.y - xq;
+                        D2[0] = fma(d0, d0, D2[0]); D2[1] = fma(d1, d1, D2[1]); D2[2] = fma(d2, d2, D2[2]); D2[3] = fma(d3, d3, D2[3]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i][t] = (KER == 1) ? D2[i] : sqrt(D2[i]);
                 }
             }
-            double raw[4], v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                raw[i] = (KER == 1) ? exp_nonpos(S[i], sExp) : __dmul_rn(Pr[i], exp_nonpos(S[i], sExp));
-                v[i] = scaled ? __dmul_rn(raw[i], a.mult) : raw[i];
+        }
+
+        const int gi0 = i0 + 4 * tx, gj = j0 + ty;
+        // which of this thread's four entries lies on the diagonal of the matrix (0..3; anything else: none)
+        const unsigned dgi = (unsigned)((a.colOff + gj) - (a.rowOff + gi0));
+        const long colOffset = (long)(a.colOff + gj) * a.ld + a.rowOff + gi0;
+        // 16-byte stores need an aligned address in every matrix of the group: an even stride keeps the alignment of the first
+        const bool full4 = gi0 + 3 < a.nP && !(a.strideM & 1) &&
+                           ((reinterpret_cast<uintptr_t>(a.M + (long)g.first * a.strideM + colOffset) & 15) == 0);
+        for (int b0 = 0; b0 < g.count; b0 += FBCH) {
+            const int nb = min(FBCH, g.count - b0);
+            if (!scalesOnce) {
+                __syncthreads();
+                stage_scales(b0, nb, nterms);
+                __syncthreads();
             }
-            if (dgi < 4u) {
+            if (gj >= a.nQ) continue;
+            double* colp = a.M + (long)(g.first + b0) * a.strideM + colOffset;
+            for (int b = 0; b < nb; ++b, colp += a.strideM) {
+                double S[4] = {0.0, 0.0, 0.0, 0.0}, Pr[4] = {1.0, 1.0, 1.0, 1.0};
+                double scv[FNT];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if ((unsigned)i == dgi) v[i] = fma(a.mult, __dadd_rn(raw[i], a.diag_rel), a.diag_abs);
-            }
-            if (full4) {
-                *reinterpret_cast<double2*>(colp) = make_double2(v[0], v[1]);
-                *reinterpret_cast<double2*>(colp + 2) = make_double2(v[2], v[3]);
-            } else {
+                for (int t = 0; t < FNT; t += 2) {
+                    const double2 s2 = *reinterpret_cast<const double2*>(&sSc[b][t]);
+                    scv[t] = s2.x; scv[t + 1] = s2.y;
+                }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (gi0 + i < a.nP) colp[i] = v[i];
+                for (int t = 0; t < FNT; ++t) {
+                    if (t < nterms) {
+                        const double sc = scv[t];
+                        if (KER == 1) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) S[i] = fma(q[i][t], sc, S[i]);
+                        } else {
+                            const double c2 = (KER == 2) ? sSc2[KER == 2 ? b : 0][t] : 0.0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) matern_term<KER>(q[i][t], sc, c2, S[i], Pr[i]);
+                        }
+                    }
+                }
+                double raw[4], v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    raw[i] = (KER == 1) ? exp_nonpos(S[i], sExp) : __dmul_rn(Pr[i], exp_nonpos(S[i], sExp));
+                    v[i] = scaled ? __dmul_rn(raw[i], a.mult) : raw[i];
+                }
+                if (dgi < 4u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if ((unsigned)i == dgi) v[i] = fma(a.mult, __dadd_rn(raw[i], a.diag_rel), a.diag_abs);
+                }
+                if (full4) {
+                    *reinterpret_cast<double2*>(colp) = make_double2(v[0], v[1]);
+                    *reinterpret_cast<double2*>(colp + 2) = make_double2(v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gi0 + i < a.nP) colp[i] = v[i];
+                }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 template <int MODE>
@@ -513,14 +555,31 @@ bool assemble_fusable(int nterms, int nunits) { return nterms >= 1 && nterms <= 
 // coordinates (groups == nullptr: one group of `count` elements).  The caller has checked assemble_fusable().
 void launch_assemble_fused(const AsmArgs& a, const AsmGroup* groups, int ngroups, int count, cudaStream_t st) {
     if (a.nP <= 0 || ngroups <= 0) return;
+    static int nsm[FGP_MAXDEV] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= FGP_MAXDEV) dev = 0;
+    if (!nsm[dev]) cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
     FusedK k{a, groups, count};
     const int nT = (a.nP + FR - 1) / FR;
-    dim3 grid((FR / FC) * nT * (nT + 1) / 2, ngroups);
+    const int ntiles = (FR / FC) * nT * (nT + 1) / 2;
+    // persistent CTAs, two per SM over the whole launch: every group gets its share of them (at least one, at most a CTA per tile)
+    const int slots = 2 * (nsm[dev] > 0 ? nsm[dev] : 148);
+    const int gx = std::max(1, std::min(ntiles, (slots + ngroups - 1) / ngroups));
+    dim3 grid(gx, ngroups);
+    constexpr int dynBytes = 2 * FCC * (FR + FC) * (int)sizeof(double);
+    static bool attr_set[FGP_MAXDEV] = {false};
+    if (!attr_set[dev]) {
+        cudaFuncSetAttribute(assemble_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynBytes);
+        cudaFuncSetAttribute(assemble_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynBytes);
+        cudaFuncSetAttribute(assemble_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynBytes);
+        attr_set[dev] = true;
+    }
     FGP_COUNT_LAUNCH();
     switch (a.ker) {
-        case 1: assemble_fused_kernel<1><<<grid, FTHREADS, 0, st>>>(k); break;
-        case 2: assemble_fused_kernel<2><<<grid, FTHREADS, 0, st>>>(k); break;
-        default: assemble_fused_kernel<3><<<grid, FTHREADS, 0, st>>>(k); break;
+        case 1: assemble_fused_kernel<1><<<grid, FTHREADS, dynBytes, st>>>(k, ntiles); break;
+        case 2: assemble_fused_kernel<2><<<grid, FTHREADS, dynBytes, st>>>(k, ntiles); break;
+        default: assemble_fused_kernel<3><<<grid, FTHREADS, dynBytes, st>>>(k, ntiles); break;
     }
 }
 
