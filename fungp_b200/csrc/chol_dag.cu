@@ -70,6 +70,7 @@ struct DagArgs {
     int hasY;                      // 1: row n holds y' and is solved along (likelihood, preMats); 0: a plain n x n matrix
     // solve mode (predict / simulate: E tiles of extra rows from row rowOff on against the T prefactored column tiles)
     int rowOff, mExtra, E;
+    int upper;                     // solve mode: the extra rows are identity rows (LOOCV): row tile r is zero left of column tile r
     double* W; long strideW;
     int* info;
     int* flagL;                    // [batch][T][T]  L(i,j) stored
@@ -251,7 +252,16 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         int i, j, b;
         constexpr bool extra = MODE != 0;
         if (!extra) dag_decode_task(task, T, B, g.G, g.matrixMajor, i, j, b);
-        else { j = task / g.E; i = T + (task - j * g.E); b = 0; }     // solve mode: column by column, the E row tiles of each
+        else if (!g.upper) { j = task / g.E; i = T + (task - j * g.E); b = 0; }     // solve mode: column by column, the E row tiles of each
+        else {
+            // identity rows (X = L^-T is upper triangular): only the tiles (r, j >= r) exist -- column j has j + 1 of them
+            j = (int)((sqrtf(8.0f * (float)task + 1.0f) - 1.0f) * 0.5f);
+            while ((j + 1) * (j + 2) / 2 <= task) ++j;
+            while (j * (j + 1) / 2 > task) --j;
+            i = T + (task - j * (j + 1) / 2); b = 0;
+        }
+        // first k-tile of the accumulation: identity rows start at their own column tile
+        const int cstart = (extra && g.upper) ? (i - T) * (FGP_TILE / KC) : 0;
         const bool diag = !extra && i == j;
         const int rowBase = extra ? g.rowOff + (i - T) * FGP_TILE : i * FGP_TILE, colBase = j * FGP_TILE;
         double* C = g.M + (long)b * g.strideM;
@@ -264,7 +274,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         // Are all inputs of this tile there already?  (The usual case away from the start and the end of the
         // factorisation.)  Then nobody polls; otherwise the producer waits k-tile by k-tile as they are flagged.
         bool ready = true;
-        for (int kt = tid; kt < j; kt += THREADS) {
+        for (int kt = (cstart >> 2) + tid; kt < j; kt += THREADS) {
             ready = ready && ld_acquire(fLi + kt) != 0;
             if (!extra) {
                 if (!diag) ready = ready && ld_acquire(fLj + kt) != 0;
@@ -312,7 +322,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             asm volatile("fence.proxy.async;\n" ::: "memory");
 #pragma unroll
             for (int s = 0; s < STAGES - 1; ++s)
-                if (s < nchunks) issue(s, gc + s);
+                if (cstart + s < nchunks) issue(cstart + s, gc + s);
         }
 
         double acc[4][8][2];
@@ -343,7 +353,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         }
 
         // ---- acc -= L(i, 0:j) L(j, 0:j)'
-        for (int c = 0; c < nchunks; ++c, ++gc) {
+        for (int c = cstart; c < nchunks; ++c, ++gc) {
             const int s = gc % STAGES;
             double yk = 0.0;
             if (ywarp) {
@@ -627,8 +637,10 @@ bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double*
 // (n columns: K(new, train)) against the factor stored in rows 0..n-1 of the same matrix and its inverse diagonal blocks
 // W -> L^-1 K(train, new) transposed, in place.  One tile task per (row tile of the block, column tile): it accumulates
 // -= X(r, 0:j) L(j, 0:j)' as the tiles of its own row are flagged and multiplies by W_j'.  flags:
-// chol_dag_solve_flag_bytes().  Returns false when the launch cannot be taken.
-bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, double* W, void* flags, cudaStream_t st) {
+// chol_dag_solve_flag_bytes().  upper: the extra rows are the n rows of an identity matrix (LOOCV: X = L^-T, upper
+// triangular -- only the tiles on and right of the diagonal are computed, each from its own column tile on).  Returns
+// false when the launch cannot be taken.
+bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, double* W, void* flags, cudaStream_t st, int upper) {
     if (n <= 0 || mExtra <= 0 || rowOff < n) return false;
     int dev, sms;
     if (!dag_prepare(&dev, &sms)) return false;
@@ -641,7 +653,9 @@ bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, do
     g.W = W; g.strideW = 0; g.info = nullptr;
     g.flagL = (int*)flags; g.flagW = g.flagL; g.flagY = g.flagL; g.counter = g.flagL + (size_t)g.E * g.T;
     if ((long)g.T * g.E > 0x7fffffffL / 2) return false;
-    g.ntasks = g.T * g.E;
+    g.upper = upper ? 1 : 0;
+    if (upper && (g.E != g.T || mExtra != n)) return false;       // identity rows: one per column
+    g.ntasks = upper ? g.T * (g.T + 1) / 2 : g.T * g.E;
     if (g.ntasks < 16) return false;      // a handful of tiles: the fixed costs of the persistent launch do not pay (measured: n = 1000, m = 10)
     CUtensorMap mapM, mapW;
     if (!make_map(&mapM, M, (long)rowOff + mExtra, n, ld, 1, 0)) return false;

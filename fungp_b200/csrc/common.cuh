@@ -118,7 +118,7 @@ size_t chol_dag_flag_bytes(int n, int batch);
 size_t chol_dag_solve_flag_bytes(int n, int mExtra);
 bool launch_chol_dag(double* M, long ld, long strideM, int batch, int n, double* W, long strideW, int* info, void* flags,
                      cudaStream_t st, int group = 1, int matrixMajor = 1, int hasY = 1);
-bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, double* W, void* flags, cudaStream_t st);
+bool launch_chol_dag_solve(double* M, long ld, int n, int rowOff, int mExtra, double* W, void* flags, cudaStream_t st, int upper = 0);
 
 struct GemmArgs {
     const double* A; long lda; long strideA;   // row operand: element (r, kk) = A[r + kk*lda], r = global row

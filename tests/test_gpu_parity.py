@@ -789,7 +789,7 @@ def test_dataflow_cholesky_is_bit_identical_at_size(ctx):
         P.close()
 
 
-@pytest.mark.parametrize("n,m", [(1407, 300), (2048, 130), (640, 1000)])
+@pytest.mark.parametrize("n,m", [(1407, 300), (2048, 130), (640, 1000), (4200, 150)])
 def test_dataflow_solve_mode_is_bit_identical(ctx, n, m):
     """predict / simulate: the rows of K(new, train) under the stored factor are eliminated by the solve mode of the
     dataflow kernel (one tile task per (row tile, column tile), flags between the tiles of a row) or, with the option
@@ -810,7 +810,9 @@ def test_dataflow_solve_mode_is_bit_identical(ctx, n, m):
             L, z = P.premats("matern5_2", 1e-8, s2[0], theta)
             pr = P.predict(m, case["sNew"], case["coefsNew"])
             sm = P.simulate(m, Z, case["sNew"], case["coefsNew"], nugget_sm=1e-8)
-            out[dag] = (L, z, pr["mean"], pr["sd"], sm["sims"], sm["mean"], sm["sd"])
+            ypre, q2 = P.loocv()            # identity rows: factor + "upper" solve mode (from n = 4096 on), or one launch-per-step pass
+            out[dag] = (L, z, pr["mean"], pr["sd"], sm["sims"], sm["mean"], sm["sd"], ypre, np.array([q2]))
+            P.premats("matern5_2", 1e-8, s2[0], theta, want_L=False)      # drops the cached leave-one-out result
     finally:
         ctx.set_option("dag", 1)
     for a, b in zip(out[0], out[1]):

@@ -28,8 +28,12 @@ for n, m in cases:
         ts = []
         for _ in range(3):
             t0 = time.perf_counter(); P.simulate(m, Z, sIn[n:], cnew, nugget_sm=1e-8); ts.append(time.perf_counter() - t0)
-        r = ref.setdefault("r", (pr["mean"], pr["sd"], sm["sims"]))
-        same = [bool(np.array_equal(a, b)) for a, b in zip(r, (pr["mean"], pr["sd"], sm["sims"]))]
-        print(f"n={n} m={m} dag={dag}: predict {min(tp)*1e3:8.3f} ms  simulate {min(ts)*1e3:8.3f} ms  identical(mean, sd, sims) {same}", flush=True)
+        tl = []
+        for _ in range(3):
+            P.premats("gauss", 1e-8, s2[0], theta, want_L=False)          # drops the cached leave-one-out result
+            t0 = time.perf_counter(); yp, q2 = P.loocv(); tl.append(time.perf_counter() - t0)
+        r = ref.setdefault("r", (pr["mean"], pr["sd"], sm["sims"], yp))
+        same = [bool(np.array_equal(a, b)) for a, b in zip(r, (pr["mean"], pr["sd"], sm["sims"], yp))]
+        print(f"n={n} m={m} dag={dag}: predict {min(tp)*1e3:8.3f} ms  simulate {min(ts)*1e3:8.3f} ms  loocv {min(tl)*1e3:8.3f} ms  identical(mean, sd, sims, loocv) {same}", flush=True)
     ctx.set_option("dag", 1)
     P.close()
