@@ -192,7 +192,7 @@ int fgp_fit_batch_holdout(fgp_ctx* ctx, int n, int ds, const double* sIn, int df
 int fgp_get_timing(fgp_ctx* ctx, double* out8);
 /* device time (CUDA events on the launching stream) of the dataflow-Cholesky launch of the last fgp_nll_batch call on
  * device 0 -- ONE kernel (csrc/chol_dag.cu) factors all matrices of the call's last chunk; 0 when that call ran on the
- * launch-per-step engine (n not a multiple of 128, option "dag" 0, profile mode) */
+ * launch-per-step engine (option "dag" 0, profile mode) */
 int fgp_last_factor_ms(fgp_ctx* ctx, double* ms);
 /* kernels of this library launched by the process so far */
 long long fgp_launch_count(void);
@@ -211,8 +211,10 @@ int fgp_elapsed_ms(fgp_ctx* ctx, int i, int j, double* ms);
  * "blocking_sync" (0/1/2, default 0: the same for this context's own calls),
  * "graphs" (0/1, default 0: batched likelihood calls at n < 2048 are captured as a CUDA graph the second time a shape is
  * seen on a problem and replayed afterwards -- one driver call per evaluation batch instead of ~30),
- * "dag" (0/1, default 1: likelihood batches, preMats and the candidate driver factor with the persistent dataflow kernel
- * csrc/chol_dag.cu when n is a multiple of 128 -- bit-identical to the launch-per-step engine it replaces),
+ * "dag" (0/1, default 1: the persistent dataflow kernel csrc/chol_dag.cu -- one launch factors all matrices of a
+ * likelihood batch / preMats / a round of the candidate driver (any n), its solve mode eliminates the new rows of
+ * predict / simulate / fgp_update_y (from 16 tiles on) and the identity rows of fgp_loocv (from n = 4096 on); results are
+ * bit-identical to the launch-per-step engine it replaces, which 0 selects everywhere),
  * "fused_assembly", "pdl", "gemm_tma" (0/1, default 1: the batch-fused assembly kernel, programmatic dependent launch,
  * TMA operand path of the DMMA GEMM), "gemm_flat" (default 8: batched GEMM launches with at least this many tiles per SM
  * and K <= 1024 run one persistent CTA per SM over all (tile, matrix) pairs; 0 = never), "la_r8", "la_r4" (look-ahead
