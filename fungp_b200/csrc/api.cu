@@ -645,11 +645,12 @@ static int nll_range(fgp_problem* P, int slot, int ker, double nugget, int b0, i
             ProblemDev& pdw = P->pd[slot];
             for (auto& g : pdw.graphs)
                 if (g.ker == ker && g.B == cb && g.nugget == nugget && g.work == d.work.p && g.wbuf == d.wbuf.p &&
-                    g.small == d.small.p && g.pinned == d.pinned && g.outer == ctx->outer) { gr = &g; break; }
+                    g.small == d.small.p && g.pinned == d.pinned && g.outer == ctx->outer && g.dag == (int)useDag &&
+                    g.dagFlags == (useDag ? d.dagFlags.p : nullptr)) { gr = &g; break; }
             if (!gr) {
                 if (pdw.graphs.size() < 8) {
                     NllGraph g; g.ker = ker; g.B = cb; g.nugget = nugget; g.work = d.work.p; g.wbuf = d.wbuf.p;
-                    g.small = d.small.p; g.pinned = d.pinned; g.outer = ctx->outer;
+                    g.small = d.small.p; g.pinned = d.pinned; g.outer = ctx->outer; g.dag = (int)useDag; g.dagFlags = useDag ? d.dagFlags.p : nullptr;
                     pdw.graphs.push_back(g);          // first sighting: run normally (also warms the launchers' statics)
                 }
             } else {

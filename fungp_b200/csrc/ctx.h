@@ -158,6 +158,7 @@ struct NllGraph {
     double nugget = 0;
     const void* work = nullptr; const void* wbuf = nullptr; const void* small = nullptr; const void* pinned = nullptr;
     int outer = 0;
+    const void* dagFlags = nullptr; int dag = 0;      // the captured sequence contains the dataflow kernel with this flag buffer
     cudaGraphExec_t exec = nullptr;     // null: seen once, not captured yet
 };
 
