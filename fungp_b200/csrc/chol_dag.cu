@@ -47,7 +47,8 @@ constexpr int BAR_OFF = RING_BYTES;                     // full[3] | empty[3]
 constexpr int WBAR_OFF = BAR_OFF + 64;                  // wfull[2]: the two W slabs of the solve
 constexpr int PBAR_OFF = WBAR_OFF + 16;                 // potf2's 32 column barriers
 constexpr int TASK_OFF = PBAR_OFF + 8 * potf2::SB;
-constexpr int AY_OFF = TASK_OFF + 16;                   // the y row of the diagonal tile in flight (128 doubles)
+constexpr int WMIN_OFF = TASK_OFF + 16;                 // per-warp minima of the ready scan (8 ints)
+constexpr int AY_OFF = WMIN_OFF + 32;                   // the y row of the diagonal tile in flight (128 doubles)
 constexpr int DAG_SMEM = AY_OFF + 8 * FGP_TILE;
 static_assert(potf2::POTF2_WORK_DOUBLES * 8 <= RING_BYTES, "potf2 works inside the ring's memory");
 static_assert(potf2::NB * potf2::LDT * 8 == 2 * STAGE * 8, "hand-over tile = stages 0 and 1");
@@ -212,6 +213,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
     const uint32_t wfullB = sbase + WBAR_OFF;
     const uint32_t pbar = sbase + PBAR_OFF;
     volatile int* sTask = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(smem) + TASK_OFF);
+    volatile int* sWarpMin = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(smem) + WMIN_OFF);
     double* ay = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + AY_OFF);
     const bool producer = tid == 0;
     if (producer) {
@@ -269,17 +271,24 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
         const int* fLj = g.flagL + ((long)b * T + j) * T;
         const int* fY = g.flagY + (long)b * T;
         const int nchunks = j * (FGP_TILE / KC);
-        // Are all inputs of this tile there already?  (The usual case away from the start and the end of the
-        // factorisation.)  Then nobody polls; otherwise the producer waits k-tile by k-tile as they are flagged.
-        bool ready = true;
+        // Which inputs of this tile are there already?  readyUpTo = the first k-tile with an input still missing (j: none
+        // -- the usual case away from the start and the end of the factorisation).  Nobody polls for the k-tiles before
+        // it; from there on the producer waits k-tile by k-tile as they are flagged.
+        int firstMissing = j;
         for (int kt = (cstart >> 2) + tid; kt < j; kt += THREADS) {
-            ready = ready && ld_acquire(fLi + kt) != 0;
+            bool ok = ld_acquire(fLi + kt) != 0;
             if (!extra) {
-                if (!diag) ready = ready && ld_acquire(fLj + kt) != 0;
-                else if (g.hasY) ready = ready && ld_acquire(fY + kt) != 0;
+                if (!diag) ok = ok && ld_acquire(fLj + kt) != 0;
+                else if (g.hasY) ok = ok && ld_acquire(fY + kt) != 0;
             }
+            if (!ok) firstMissing = min(firstMissing, kt);
         }
-        const bool allReady = __syncthreads_and(ready) != 0;
+        firstMissing = __reduce_min_sync(0xffffffffu, firstMissing);
+        if (lane == 0) sWarpMin[warp] = firstMissing;
+        __syncthreads();                                    // (also: everybody has read the task slot)
+        int readyUpTo = sWarpMin[0];
+#pragma unroll
+        for (int w = 1; w < MMA_WARPS; ++w) readyUpTo = min(readyUpTo, sWarpMin[w]);
 #ifdef FGP_DAG_PROF
         DPROF(0, tPh); tPh = clock64();
         if (threadIdx.x == 0) { atomicAdd(&g_dag_prof[4], 1ULL); if (diag) atomicAdd(&g_dag_prof[5], 1ULL); }
@@ -304,7 +313,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 
         // the producer's request for chunk cl of this tile (ring position G)
         auto issue = [&](int cl, int G) {
-            if (!allReady && (cl & 3) == 0) {
+            if ((cl & 3) == 0 && (cl >> 2) >= readyUpTo) {
                 wait_flag(fLi + (cl >> 2));
                 if (!diag && !extra) wait_flag(fLj + (cl >> 2));
             }
@@ -355,7 +364,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
             const int s = gc % STAGES;
             double yk = 0.0;
             if (ywarp) {
-                if (!allReady && (c & 3) == 0) {
+                if ((c & 3) == 0 && (c >> 2) >= readyUpTo) {
                     const long long t0 = clock64();
                     while (ld_acquire(fY + (c >> 2)) == 0) {
                         __nanosleep(64);
