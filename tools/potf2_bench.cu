@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
     for (int s = 0; s < 4; ++s)
         printf("s=%d: (c of s-1 | a) %lld  (b) %lld  cycles  [%lld]\n", s, p[2 + 3 * s] - p[1 + 3 * s], p[3 + 3 * s] - p[2 + 3 * s],
                (s < 3 ? p[4 + 3 * s] : p[13]) - p[3 + 3 * s]);
-    printf("store L %lld  store W %lld  total %lld cycles\n", p[14] - p[13], p[15] - p[14], p[15] - p[0]);
+    printf("store W %lld  store L %lld  total %lld cycles\n", p[14] - p[13], p[15] - p[14], p[15] - p[0]);      // W goes first (potf2_body.cuh)
     std::vector<double> o(h.size());
     cudaMemcpy(o.data(), M, sizeof(double) * h.size(), cudaMemcpyDeviceToHost);
     // residual check of the first matrix
