@@ -30,6 +30,8 @@
 #include "potf2_body.cuh"
 #include <cuda.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 namespace {
 
@@ -537,7 +539,7 @@ chol_dag_kernel(DagArgs g, const __grid_constant__ CUtensorMap mapM, const __gri
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-bool g_encode_tried = false;
+std::once_flag g_encode_once;
 
 // 3-D map over a column-major operand: (rows, k, batch element); box = PITCH rows x KC k x 1
 bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, long batch, long strideElems) {
@@ -581,16 +583,16 @@ size_t chol_dag_solve_flag_bytes(int n, int mExtra) {
 
 namespace {
 bool dag_prepare(int* dev_out, int* sms_out) {
-    static bool attr_set[FGP_MAXDEV] = {false};
-    static int nsm[FGP_MAXDEV] = {0};
-    if (!g_encode_tried) {
-        g_encode_tried = true;
+    static std::atomic<bool> attr_set[FGP_MAXDEV];        // zero-initialised; setting the attribute twice is harmless
+    static std::atomic<int> nsm[FGP_MAXDEV];
+    // (several host threads -- one per GPU of a context, the worker contexts of fgp_fit_batch -- may arrive here at once)
+    std::call_once(g_encode_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             g_encode = (EncodeTiledFn)fn;
         else cudaGetLastError();
-    }
+    });
     if (!g_encode) return false;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -601,11 +603,14 @@ bool dag_prepare(int* dev_out, int* sms_out) {
             cudaGetLastError();
             return false;
         }
-        cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
+        int count = 0;
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+        nsm[dev] = count;
         attr_set[dev] = true;
     }
     *dev_out = dev;
-    *sms_out = nsm[dev] > 0 ? nsm[dev] : 148;
+    const int count = nsm[dev];
+    *sms_out = count > 0 ? count : 148;
     return true;
 }
 }  // namespace

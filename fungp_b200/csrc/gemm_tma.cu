@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 namespace {
 
@@ -331,7 +333,7 @@ gemm_dmma_tma_kernel(GemmArgs g, int ntiles, int flat, const __grid_constant__ C
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-bool g_encode_tried = false;
+std::once_flag g_encode_once;
 
 // 3-D map over a column-major operand: (rows, k, batch element); box = PITCH rows x KC k x 1
 bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, long batch, long strideElems) {
@@ -349,16 +351,16 @@ bool make_map(CUtensorMap* m, const double* base, long rows, long K, long ld, lo
 // returns false when the TMA path cannot take this launch (driver entry point missing, operand not 16-byte aligned):
 // the caller then uses the cp.async kernel
 bool launch_gemm_tma(const GemmArgs& g, cudaStream_t st) {
-    static bool attr_set[FGP_MAXDEV] = {false};
-    static int nsm[FGP_MAXDEV] = {0};
-    if (!g_encode_tried) {
-        g_encode_tried = true;
+    static std::atomic<bool> attr_set[FGP_MAXDEV];        // zero-initialised; setting the attribute twice is harmless
+    static std::atomic<int> nsm[FGP_MAXDEV];
+    // (several host threads -- one per GPU of a context, the worker contexts of fgp_fit_batch -- may arrive here at once)
+    std::call_once(g_encode_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
             g_encode = (EncodeTiledFn)fn;
         else cudaGetLastError();
-    }
+    });
     if (!g_encode) return false;
     if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda & 1) || (g.ldb & 1) || (g.strideA & 1) || (g.strideB & 1)) return false;
     const int ntiles = g.triT * (g.triT + 1) / 2 + (g.rectNR + g.rectNR1) * g.rectNC;
@@ -371,14 +373,17 @@ bool launch_gemm_tma(const GemmArgs& g, cudaStream_t st) {
             cudaGetLastError();
             return false;
         }
-        cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
+        int count = 0;
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+        nsm[dev] = count;
         attr_set[dev] = true;
     }
     CUtensorMap mapA, mapB;
     // rows beyond the logical extent are outside the map (zero-filled); k beyond K likewise
     const long rowsA = g.nrows, rowsB = g.bLowerTri ? FGP_TILE : g.ncols;
     if (!make_map(&mapA, g.A, rowsA, g.K, g.lda, g.batch, g.strideA) || !make_map(&mapB, g.B, rowsB, g.K, g.ldb, g.batch, g.strideB)) return false;
-    const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
+    const int smCount = nsm[dev];
+    const int sms = smCount > 0 ? smCount : 148;
     int tpc = std::max(1, std::min(16, 3072 / std::max(1, g.K)));       // tiles per CTA: K=128 -> 16 ... K>=2048 -> 1
     if (g.maxTilesPerCta > 0) tpc = std::min(tpc, g.maxTilesPerCta);
     int gx = ntiles;
