@@ -20,6 +20,7 @@
 // coordinate and entry plus an 18-instruction exp against 8 bytes written, on a machine whose DFMA and DMMA share
 // one FP64 datapath (profiles/r01_peaks.md) -- see DESIGN.md 2.3 for the count.
 #include "common.cuh"
+#include <atomic>
 #include <algorithm>
 
 namespace {
@@ -555,20 +556,25 @@ bool assemble_fusable(int nterms, int nunits) { return nterms >= 1 && nterms <= 
 // coordinates (groups == nullptr: one group of `count` elements).  The caller has checked assemble_fusable().
 void launch_assemble_fused(const AsmArgs& a, const AsmGroup* groups, int ngroups, int count, cudaStream_t st) {
     if (a.nP <= 0 || ngroups <= 0) return;
-    static int nsm[FGP_MAXDEV] = {0};
+    static std::atomic<int> nsm[FGP_MAXDEV];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= FGP_MAXDEV) dev = 0;
-    if (!nsm[dev]) cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (!nsm[dev]) {
+        int count = 0;
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+        nsm[dev] = count;
+    }
     FusedK k{a, groups, count};
     const int nT = (a.nP + FR - 1) / FR;
     const int ntiles = (FR / FC) * nT * (nT + 1) / 2;
     // persistent CTAs, two per SM over the whole launch: every group gets its share of them (at least one, at most a CTA per tile)
-    const int slots = 2 * (nsm[dev] > 0 ? nsm[dev] : 148);
+    const int smCount = nsm[dev];
+    const int slots = 2 * (smCount > 0 ? smCount : 148);
     const int gx = std::max(1, std::min(ntiles, (slots + ngroups - 1) / ngroups));
     dim3 grid(gx, ngroups);
     constexpr int dynBytes = 2 * FCC * (FR + FC) * (int)sizeof(double);
-    static bool attr_set[FGP_MAXDEV] = {false};
+    static std::atomic<bool> attr_set[FGP_MAXDEV];        // zero-initialised; several host threads may arrive at once
     if (!attr_set[dev]) {
         cudaFuncSetAttribute(assemble_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynBytes);
         cudaFuncSetAttribute(assemble_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynBytes);

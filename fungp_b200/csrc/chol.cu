@@ -10,6 +10,7 @@
 // holding K(new, train) turn into (L^-1 K.tp)', and -- when the matrix also has the K(new,new) columns --
 // the trailing update leaves the Schur complement there, which the same loop then factors.
 #include "common.cuh"
+#include <atomic>
 #include "ctx.h"
 #include <functional>
 
@@ -515,7 +516,7 @@ void launch_copy_row(double* M, long ld, int ncol, int src, int dst, cudaStream_
     copy_row_kernel<<<cdiv(ncol, 256), 256, 0, st>>>(M, ld, ncol, src, dst);
 }
 void launch_trtri_blocks(const double* M, long ld, int n, double* W, cudaStream_t st) {
-    static bool attr_set[FGP_MAXDEV] = {false};
+    static std::atomic<bool> attr_set[FGP_MAXDEV];        // zero-initialised; several host threads may arrive at once
     const int smem = FGP_TILE * 129 * (int)sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);

@@ -11,6 +11,7 @@
 // shared memory by cp.async in a [row-block of 8][k][8 rows] layout that makes every fragment load a
 // conflict-free 256-byte LDS.64, 3-stage pipeline over K chunks of 32.
 #include "common.cuh"
+#include <atomic>
 #include <algorithm>
 
 #ifdef FGP_GEMM_DEBUG
@@ -389,21 +390,24 @@ bool launch_gemm_tma(const GemmArgs& g, cudaStream_t st);
 void launch_gemm(const GemmArgs& g, cudaStream_t st) {
     // TMA operand path (gemm_tma.cu): same numerics; falls back here when it cannot take the launch
     if (g.tma && launch_gemm_tma(g, st)) return;
-    static bool attr_set[FGP_MAXDEV] = {false};
-    static int nsm[FGP_MAXDEV] = {0};
+    static std::atomic<bool> attr_set[FGP_MAXDEV];        // zero-initialised; several host threads may arrive at once
+    static std::atomic<int> nsm[FGP_MAXDEV];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= FGP_MAXDEV) dev = 0;
     if (!attr_set[dev]) {
         cudaFuncSetAttribute(gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM + 64);
-        cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev);
+        int count = 0;
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+        nsm[dev] = count;
         attr_set[dev] = true;
     }
     const int ntiles = g.triT * (g.triT + 1) / 2 + (g.rectNR + g.rectNR1) * g.rectNC;
     if (ntiles <= 0 || g.batch <= 0) return;
     // semi-persistent: a CTA walks several tiles (operand prefetch across tile boundaries), but holds its SM for at
     // most ~0.4 ms so that other streams' panel kernels (diagonal block, panel solve) get an SM quickly
-    const int sms = nsm[dev] > 0 ? nsm[dev] : 148;
+    const int smCount = nsm[dev];
+    const int sms = smCount > 0 ? smCount : 148;
     int tpc = std::max(1, std::min(16, 3072 / std::max(1, g.K)));       // tiles per CTA: K=128 -> 16 ... K>=2048 -> 1
     if (g.maxTilesPerCta > 0) tpc = std::min(tpc, g.maxTilesPerCta);
     // whole waves: with more CTAs than SMs the grid is rounded up to a multiple of the SM count, otherwise the last,

@@ -1,6 +1,7 @@
 // Diagonal-block kernel of the blocked Cholesky: one launch factors the 128x128 block (L_kk) of every matrix of the
 // batch and produces its inverse W_k = inv(L_kk).  The algorithm is in potf2_body.cuh.
 #include "potf2_body.cuh"
+#include <atomic>
 
 namespace {
 using namespace potf2;
@@ -25,7 +26,7 @@ potf2_inv_kernel(double* M, long ld, long strideM, int k0, int nb, double* W, lo
 
 void launch_potf2(double* M, long ld, long strideM, int batch, int k0, int nb, double* W, long strideW, int* info,
                   int infoOff, cudaStream_t st, int pdl) {
-    static bool attr_set[FGP_MAXDEV] = {false};
+    static std::atomic<bool> attr_set[FGP_MAXDEV];        // zero-initialised; several host threads may arrive at once
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < FGP_MAXDEV && !attr_set[dev]) {
